@@ -1,0 +1,218 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(cholespy_b200's Python mirror is a ctypes binding of include/cholespy_b200.h)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.linalg import spsolve
+
+import problems
+from helpers import GOLDEN_CASES, TOL, factorize, load_golden, max_rel_err, rel_residual
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from cholespy_b200 import CholeskySolverD, CholeskySolverF, MatrixType, _capi  # noqa: E402
+
+RHS = [1, 4, 16, 64, 128, 256]
+
+
+def _solver(p, dtype, device="cuda"):
+    cls = CholeskySolverF if np.dtype(dtype) == np.float32 else CholeskySolverD
+    return cls(p["n"], torch.tensor(p["ii"], device=device), torch.tensor(p["jj"], device=device),
+               torch.tensor(p["x"], device=device), getattr(MatrixType, p["fmt"]))
+
+
+def _gpu_solve(solver, b):
+    bt = torch.tensor(b, device="cuda")
+    xt = torch.zeros_like(bt)
+    solver.solve(bt, xt)
+    torch.cuda.synchronize()
+    assert np.array_equal(bt.cpu().numpy(), b), "b must not be modified"
+    return xt.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_analysis_and_permutation_bit_exact_vs_golden(case):
+    g = load_golden(case)
+    p = dict(n=int(g["n"]), ii=g["ii"], jj=g["jj"], x=g["x"], fmt=str(g["fmt"]))
+    s = _solver(p, np.float64)
+    assert np.array_equal(s.permutation(), g["perm"])
+    lo, lo_order = s.analysis(lower=True)
+    up, up_order = s.analysis(lower=False)
+    assert np.array_equal(lo, g["lower_level"]) and np.array_equal(lo_order, g["lower_order"])
+    assert np.array_equal(up, g["upper_level"]) and np.array_equal(up_order, g["upper_order"])
+    info = s.info()
+    assert [info["n_levels_lower"], info["n_levels_upper"]] == list(g["n_levels"])
+    # and the solution against the reference's own CPU solve stored in the fixture
+    x = _gpu_solve(s, g["b"])
+    assert max_rel_err(x, g["x_ref_cpu"]) < TOL[np.dtype(np.float64)]
+    s32 = _solver(p, np.float32)
+    x32 = _gpu_solve(s32, g["b"].astype(np.float32))
+    assert max_rel_err(x32, g["x_ref_cpu"]) < TOL[np.dtype(np.float32)]
+
+
+@pytest.mark.parametrize("name", ["ico5", "grid2d-64", "grid3d-12", "localspd-40"])
+def test_analysis_bit_exact_vs_oracle(name, oracle_mod, native_lib):
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    rp, ci, _ = oracle_mod.csc_to_csr(cp, ri, v)
+    lo_ref, lo_n, lo_order_ref = oracle_mod.levels(rp, ci, False)
+    up_ref, up_n, up_order_ref = oracle_mod.levels(cp, ri, True)
+    s = _solver(p, np.float32)
+    lo, lo_order = s.analysis(True)
+    up, up_order = s.analysis(False)
+    assert np.array_equal(s.permutation(), perm)
+    assert np.array_equal(lo, lo_ref) and np.array_equal(lo_order, lo_order_ref)
+    assert np.array_equal(up, up_ref) and np.array_equal(up_order, up_order_ref)
+    info = s.info()
+    assert (info["n_levels_lower"], info["n_levels_upper"]) == (lo_n, up_n)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["cube", "ico3", "ico5", "grid2d-40"])
+def test_solve_vs_oracle_all_rhs_widths(name, dtype, oracle_mod, native_lib):
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    A = problems.to_scipy_csc(p)
+    rng = np.random.default_rng(45)
+    ks = [1, 2, 3, 4, 5, 8, 9, 16, 31, 32, 33, 64, 100, 128]
+    b_all = rng.random((p["n"], max(ks))).astype(dtype)
+    x_or_all = oracle_mod.solve(cp, ri, v, perm, b_all)
+    s = _solver(p, dtype)
+    tol = TOL[np.dtype(dtype)]
+    for k in ks:  # one solver instance, changing widths (exercises the work-vector reallocation)
+        b = np.ascontiguousarray(b_all[:, :k])
+        x = _gpu_solve(s, b)
+        x_or = x_or_all[:, :k]
+        assert max_rel_err(x, x_or) < tol, (name, k)
+        assert rel_residual(A, x, b) < (1e-5 if dtype == np.float32 else 1e-13), (name, k)
+    # 1-D right-hand side
+    x1 = _gpu_solve(s, np.ascontiguousarray(b_all[:, 0]))
+    assert max_rel_err(x1, x_or_all[:, 0]) < tol
+
+
+# Mirrors reference tests/test_cholesky.py:10-44 for device == "cuda".
+@pytest.mark.parametrize("mesh", ["cube", "ico3", "ico5"])
+@pytest.mark.parametrize("variant", ["float", "double"])
+def test_solver_cuda_like_reference(variant, mesh):
+    np.random.seed(45)
+    dtype = np.float32 if variant == "float" else np.float64
+    Solver = CholeskySolverF if variant == "float" else CholeskySolverD
+    n_verts, faces = problems.cube() if mesh == "cube" else problems.icosphere(int(mesh[3:]))
+    values, idx = problems.mesh_laplacian_coo(n_verts, faces, 2.0)
+    L_csc = sp.csc_matrix((values, idx))
+    b = np.random.random(size=(n_verts, max(RHS))).astype(dtype)
+    x = spsolve(L_csc, b)
+    solver = Solver(n_verts, torch.tensor(idx[0], device="cuda"), torch.tensor(idx[1], device="cuda"),
+                    torch.tensor(values, device="cuda"), MatrixType.COO)
+    for n_rhs in RHS:
+        b_torch = torch.tensor(b[:, :n_rhs], device="cuda")
+        x_torch = torch.zeros_like(b_torch)
+        try:
+            solver.solve(b_torch, x_torch)
+            assert n_rhs <= 128
+            assert np.allclose(x_torch.cpu().numpy(), x[:, :n_rhs])
+        except ValueError as e:
+            assert n_rhs > 128
+            assert str(e) == "The number of RHS should be less than 128."
+
+
+# Mirrors reference tests/test_cholesky.py:46-86 for device == "cuda".
+def test_matrices_cuda_like_reference():
+    np.random.seed(45)
+    n_verts, faces = problems.cube()
+    values, idx = problems.mesh_laplacian_coo(n_verts, faces, 2.0)
+    L_csc = sp.csc_matrix((values, idx))
+    L_csr = sp.csr_matrix((values, idx))
+    b = np.random.random(size=(n_verts, 32)).astype(np.float32)
+    b_torch = torch.tensor(b, device="cuda")
+    x_ref = spsolve(L_csc, b)
+    for args in [(idx[0], idx[1], values, MatrixType.COO), (L_csr.indptr, L_csr.indices, L_csr.data, MatrixType.CSR),
+                 (L_csc.indptr, L_csc.indices, L_csc.data, MatrixType.CSC)]:
+        solver = CholeskySolverF(n_verts, *[torch.tensor(a, device="cuda") for a in args[:3]], args[3])
+        x_torch = torch.zeros_like(b_torch)
+        solver.solve(b_torch, x_torch)
+        assert np.allclose(x_torch.cpu().numpy(), x_ref)
+
+
+def test_device_mismatch_errors():
+    p = problems.build_problem("cube")
+    s = _solver(p, np.float32)
+    b = np.zeros((p["n"], 2), np.float32)
+    with pytest.raises(ValueError, match="Input device is CPU but the solver was initialized for CUDA."):
+        s.solve(b, np.zeros_like(b))
+    with pytest.raises(ValueError, match="x and b should be on the same device."):
+        s.solve(torch.tensor(b, device="cuda"), torch.tensor(b))
+    cpu = CholeskySolverF(p["n"], p["ii"], p["jj"], p["x"], MatrixType.COO)
+    with pytest.raises(ValueError, match="Input device is CUDA but the solver was initialized for CPU."):
+        cpu.solve(torch.tensor(b, device="cuda"), torch.tensor(b, device="cuda"))
+    with pytest.raises(ValueError, match="All input tensors should be on the same device!"):
+        CholeskySolverF(p["n"], torch.tensor(p["ii"], device="cuda"), torch.tensor(p["jj"]), torch.tensor(p["x"]),
+                        MatrixType.COO)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_against_reference_gpu_kernels(dtype, oracle_mod):
+    """The reference's own class and kernels (compiled unmodified, oracle/_ref) on the same GPU:
+    level schedule and permutation bit-exact, solutions within the stated tolerance."""
+    if not oracle_mod.reference_available():
+        pytest.skip("oracle/_ref not present")
+    p = problems.build_problem("ico5")
+    try:
+        ref = oracle_mod.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False)
+    except RuntimeError:
+        ref = oracle_mod.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False, use_sm100_cubin=True)
+    s = _solver(p, dtype)
+    lo_ref, up_ref, perm_ref = ref.schedule()
+    assert np.array_equal(s.permutation(), perm_ref)
+    assert np.array_equal(s.analysis(True)[1], lo_ref)
+    assert np.array_equal(s.analysis(False)[1], up_ref)
+    rng = np.random.default_rng(11)
+    for k in (1, 3, 32, 128):
+        b = rng.random((p["n"], k)).astype(dtype)
+        bt = torch.tensor(b, device="cuda")
+        xr = torch.zeros_like(bt)
+        ref.solve_cuda(k, bt.data_ptr(), xr.data_ptr())
+        torch.cuda.synchronize()
+        x = _gpu_solve(s, b)
+        err = max_rel_err(x, xr.cpu().numpy())
+        assert err < TOL[np.dtype(dtype)], (k, err)
+
+
+def test_solve_host_end_to_end(oracle_mod, native_lib):
+    p = problems.build_problem("ico4")
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    s = _solver(p, np.float64)
+    b = np.random.default_rng(5).random((p["n"], 6))
+    x = np.zeros_like(b)
+    s.solve_host(b, x)
+    assert max_rel_err(x, oracle_mod.solve(cp, ri, v, perm, b)) < 1e-12
+
+
+def test_from_factor_entry_point(oracle_mod, native_lib):
+    import ctypes
+    g = load_golden("ico3")
+    h = ctypes.c_void_p()
+    _capi.check(native_lib.chb_solver_create_from_factor(
+        ctypes.byref(h), _capi.F64, int(g["n"]), len(g["l_rowidx"]), g["l_colptr"].ctypes.data, g["l_rowidx"].ctypes.data,
+        g["l_vals"].ctypes.data, g["perm"].ctypes.data, 0))
+    s = CholeskySolverD._from_handle(h, int(g["n"]), 0)
+    x = _gpu_solve(s, g["b"])
+    assert max_rel_err(x, g["x_ref_cpu"]) < 1e-12
+
+
+def test_repeated_solves_are_deterministic_and_linear():
+    """Size-independent properties at a larger size: repeatability, linearity, residual."""
+    p = problems.build_problem("ico7")
+    A = problems.to_scipy_csc(p)
+    s = _solver(p, np.float64)
+    rng = np.random.default_rng(1)
+    b1, b2 = rng.random((p["n"], 4)), rng.random((p["n"], 4))
+    x1, x2 = _gpu_solve(s, b1), _gpu_solve(s, b2)
+    assert np.array_equal(_gpu_solve(s, b1), x1)
+    x12 = _gpu_solve(s, b1 + 2.0 * b2)
+    assert max_rel_err(x12, x1 + 2.0 * x2) < 1e-12
+    assert rel_residual(A, x1, b1) < 1e-13
+    s32 = _solver(p, np.float32)
+    xf = _gpu_solve(s32, b1.astype(np.float32))
+    assert max_rel_err(xf, x1) < 1e-5
