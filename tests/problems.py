@@ -104,13 +104,8 @@ def local_random_spd(side, draws=4, radius=1, seed=7):
 # ------------------------------------------------------------------------------------------------
 # BASELINE.json configs -> (name, n, (ii, jj, x, MatrixType name), dtype, n_rhs, scipy matrix)
 # ------------------------------------------------------------------------------------------------
-def build_problem(name):
-    """Returns dict(n, ii, jj, x, fmt, dtype, k, A) for a named workload.
-
-    names: cube, ico<L>[f|d]-k<K>, grid2d-<m>, grid3d-<m>, localspd-<side>, and the aliases
-    cfg1..cfg5 for BASELINE.json's configs (cfg3 -> 3-D grid 64^3 stand-in unless CHB_CFG3_SIDE is
-    set; cfg5 -> the locality-structured stand-in).  k/dtype can be overridden by the caller.
-    """
+def resolve_workload(name):
+    """(generator name, dtype 'f'|'d', n_rhs) of a workload name or BASELINE alias, without building it."""
     import os
     alias = {
         "cfg1": ("grid2d-256", "d", 1),
@@ -119,9 +114,17 @@ def build_problem(name):
         "cfg4": ("ico9", "f", 128),
         "cfg5": ("localspd-1000", "d", 128),
     }
-    dtype, k = "f", 1
-    if name in alias:
-        name, dtype, k = alias[name]
+    return alias.get(name, (name, "f", 1))
+
+
+def build_problem(name):
+    """Returns dict(n, ii, jj, x, fmt, dtype, k, A) for a named workload.
+
+    names: cube, ico<L>[f|d]-k<K>, grid2d-<m>, grid3d-<m>, localspd-<side>, and the aliases
+    cfg1..cfg5 for BASELINE.json's configs (cfg3 -> 3-D grid 64^3 stand-in unless CHB_CFG3_SIDE is
+    set; cfg5 -> the locality-structured stand-in).  k/dtype can be overridden by the caller.
+    """
+    name, dtype, k = resolve_workload(name)
     if name == "cube":
         n, faces = cube()
         vals, idx = mesh_laplacian_coo(n, faces, 2.0)

@@ -151,24 +151,58 @@ def test_device_mismatch_errors():
                         MatrixType.COO)
 
 
+def _reference_gpu(oracle_mod, p, dtype):
+    try:
+        return oracle_mod.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False)
+    except RuntimeError:  # driver refused the reference's sm_30 PTX: same kernels compiled for sm_100a
+        return oracle_mod.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False, use_sm100_cubin=True)
+
+
+def test_schedule_against_reference_gpu_analysis(oracle_mod, native_lib):
+    """Level schedule and permutation of the reference's own class + kernels (compiled unmodified,
+    oracle/_ref) on the same GPU.
+
+    The reference's analysis kernels publish `row_levels[row]` and `analyzed_rows[row]` with two
+    unordered volatile stores (kernels/kernels.cu:28-29), so on a B200 a waiting row can read a stale
+    level: its output varies from run to run on larger inputs and is sometimes not even a valid
+    topological order (measured: scripts/diag_ref_levels.py, profiles/r01_reference_analysis_race.txt).
+    Whenever the race does not fire the reference's arrays must equal ours bit for bit; on the small
+    case it never fires.
+    """
+    if not oracle_mod.reference_available():
+        pytest.skip("oracle/_ref not present")
+    for name, must_match in (("ico3", True), ("ico5", False)):
+        p = problems.build_problem(name)
+        s = _solver(p, np.float32)
+        mine_lo, mine_up = s.analysis(True)[1], s.analysis(False)[1]
+        lvl_lo, lvl_up = s.analysis(True)[0], s.analysis(False)[0]
+        matched = False
+        for _ in range(6):
+            ref = _reference_gpu(oracle_mod, p, np.float32)
+            lo_ref, up_ref, perm_ref = ref.schedule()
+            ref.close()
+            assert np.array_equal(s.permutation(), perm_ref)
+            for ours, theirs, lvl in ((mine_lo, lo_ref, lvl_lo), (mine_up, up_ref, lvl_up)):
+                race_free = bool(np.all(np.diff(lvl[theirs]) >= 0))  # rows grouped by true level
+                if race_free:
+                    assert np.array_equal(ours, theirs)
+            if np.array_equal(mine_lo, lo_ref) and np.array_equal(mine_up, up_ref):
+                matched = True
+                break
+        assert matched or not must_match, name
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_against_reference_gpu_kernels(dtype, oracle_mod):
-    """The reference's own class and kernels (compiled unmodified, oracle/_ref) on the same GPU:
-    level schedule and permutation bit-exact, solutions within the stated tolerance."""
+def test_solutions_against_reference_gpu_kernels(dtype, oracle_mod):
+    """Solutions of the reference's own GPU kernels on the same inputs, within the stated tolerance;
+    the wide kernels (k > 8) keep the reference's summation order and are expected bit-identical."""
     if not oracle_mod.reference_available():
         pytest.skip("oracle/_ref not present")
     p = problems.build_problem("ico5")
-    try:
-        ref = oracle_mod.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False)
-    except RuntimeError:
-        ref = oracle_mod.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False, use_sm100_cubin=True)
+    ref = _reference_gpu(oracle_mod, p, dtype)
     s = _solver(p, dtype)
-    lo_ref, up_ref, perm_ref = ref.schedule()
-    assert np.array_equal(s.permutation(), perm_ref)
-    assert np.array_equal(s.analysis(True)[1], lo_ref)
-    assert np.array_equal(s.analysis(False)[1], up_ref)
     rng = np.random.default_rng(11)
-    for k in (1, 3, 32, 128):
+    for k in (1, 3, 8, 16, 32, 100, 128):
         b = rng.random((p["n"], k)).astype(dtype)
         bt = torch.tensor(b, device="cuda")
         xr = torch.zeros_like(bt)
@@ -177,6 +211,8 @@ def test_against_reference_gpu_kernels(dtype, oracle_mod):
         x = _gpu_solve(s, b)
         err = max_rel_err(x, xr.cpu().numpy())
         assert err < TOL[np.dtype(dtype)], (k, err)
+        if k > 8:
+            assert np.array_equal(x, xr.cpu().numpy()), "wide kernel lost bit-exactness with the reference (k=%d)" % k
 
 
 def test_solve_host_end_to_end(oracle_mod, native_lib):
