@@ -222,7 +222,7 @@ def build_solver(args, name, p, k, dtype, rank, world, device):
     cls = CholeskySolverF if dtype == np.float32 else CholeskySolverD
     code = _capi.F32 if dtype == np.float32 else _capi.F64
     handle = ctypes.c_void_p()
-    meta = torch.zeros(4, dtype=torch.int64, device=device)
+    meta = torch.zeros(_capi.IMAGE_SHAPE_WORDS, dtype=torch.int64, device=device)
     t_build = None
     if rank == 0:
         perm, cp, ri, v = get_factor(name, p)
@@ -233,16 +233,20 @@ def build_solver(args, name, p, k, dtype, rank, world, device):
         t_build = time.time() - t
         solver = cls._from_handle(handle, len(perm), device.index)
         info = solver.info()
-        meta = torch.tensor([info["n"], info["nnz_l"], info["n_levels_lower"], info["n_levels_upper"]], dtype=torch.int64,
-                            device=device)
-        log("device image built in %.1f s: n=%d nnz(L)=%d levels=%d/%d" % (t_build, info["n"], info["nnz_l"],
-                                                                             info["n_levels_lower"], info["n_levels_upper"]))
+        shape = (ctypes.c_int64 * _capi.IMAGE_SHAPE_WORDS)()
+        _capi.check(lib.chb_solver_image_shape(handle, shape, _capi.IMAGE_SHAPE_WORDS))
+        meta = torch.tensor(list(shape), dtype=torch.int64, device=device)
+        log("device image built in %.1f s: n=%d nnz(L)=%d levels=%d/%d tasks=%d/%d slab=%.1f/%.1f MB" % (
+            t_build, info["n"], info["nnz_l"], info["n_levels_lower"], info["n_levels_upper"], info["fwd_tasks"],
+            info["bwd_tasks"], info["fwd_slab_bytes"] / 1e6, info["bwd_slab_bytes"] / 1e6))
     if world > 1:
         dist.broadcast(meta, src=0)
-        n, z, nl, nu = [int(v) for v in meta.tolist()]
+        words = [int(v) for v in meta.tolist()]
+        n = words[0]
         if rank != 0:
             _capi.check(lib.chb_init(device.index))
-            _capi.check(lib.chb_solver_create_replica(ctypes.byref(handle), code, n, z, nl, nu, device.index))
+            shape = (ctypes.c_int64 * _capi.IMAGE_SHAPE_WORDS)(*words)
+            _capi.check(lib.chb_solver_create_replica(ctypes.byref(handle), code, shape, _capi.IMAGE_SHAPE_WORDS, device.index))
             solver = cls._from_handle(handle, n, device.index)
         torch.cuda.synchronize()
         t = time.time()
@@ -254,7 +258,7 @@ def build_solver(args, name, p, k, dtype, rank, world, device):
         if rank == 0:
             log("NCCL broadcast of the device image: %.1f MB in %.1f ms" % (total / 1e6, 1e3 * (time.time() - t)))
     n, z = int(meta[0]), int(meta[1])
-    return solver, n, z, (int(meta[2]), int(meta[3]))
+    return solver, n, z, (int(meta[10]), int(meta[11]))
 
 
 def run_b200(args, name, p, k_total, dtype):

@@ -202,9 +202,11 @@ class _CholeskySolver:
         _capi.check(_capi.load().chb_solver_solve_host(self._handle, n_rhs, a_b.ptr, a_x.ptr))
 
     def info(self):
-        out = (ctypes.c_int64 * 8)()
-        m = _capi.load().chb_solver_info(self._handle, out, 8)
-        keys = ("n", "nnz_l", "n_levels_lower", "n_levels_upper", "dtype", "device", "grid", "launches_per_solve")
+        out = (ctypes.c_int64 * 18)()
+        m = _capi.load().chb_solver_info(self._handle, out, 18)
+        keys = ("n", "nnz_l", "n_levels_lower", "n_levels_upper", "dtype", "device", "grid", "launches_per_solve",
+                "fwd_tasks", "fwd_slab_bytes", "fwd_slots", "fwd_task_levels", "fwd_stored_values",
+                "bwd_tasks", "bwd_slab_bytes", "bwd_slots", "bwd_task_levels", "bwd_stored_values")
         return dict(zip(keys[:m], list(out)[:m]))
 
     def analysis(self, lower=True):

@@ -8,6 +8,7 @@ _LIB_PATH = os.path.join(_LIB_DIR, "libcholespy_b200.so")
 OK, ERR_INVALID, ERR_RUNTIME = 0, 1, 2
 F32, F64 = 0, 1
 DEVICE_CPU = -1
+IMAGE_SHAPE_WORDS = 12
 
 _lib = None
 
@@ -27,8 +28,9 @@ _SIGNATURES = {
                                                             ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int]),
     "chb_solver_create_from_factor": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_vp,
                                                      c_vp, c_vp, c_vp, ctypes.c_int]),
-    "chb_solver_create_replica": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int64,
-                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "chb_solver_image_shape": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "chb_solver_create_replica": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                                 ctypes.c_int, ctypes.c_int]),
     "chb_solver_destroy": (None, [c_vp]),
     "chb_solver_solve_cuda": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
     "chb_solver_solve_host": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
@@ -45,6 +47,11 @@ _SIGNATURES = {
     "chb_solver_image_count": (ctypes.c_int, [c_vp]),
     "chb_solver_image_buffer": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_vp),
                                                ctypes.POINTER(ctypes.c_uint64)]),
+    "chb_schedule_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_vp, c_vp, c_vp,
+                                           c_vp, ctypes.c_int]),
+    "chb_schedule_sweep": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                          ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "chb_schedule_destroy": (None, [c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -10,6 +10,7 @@
 #include "cholesky_solver.h"
 #include "factor_host.h"
 #include "gpu_solver.h"
+#include "panel_schedule.h"
 
 #define CHB_API extern "C" __attribute__((visibility("default")))
 
@@ -24,6 +25,11 @@ struct chb_solver {
 
 struct chb_factor {
     chb::HostFactor L;
+};
+
+struct chb_schedule {
+    chb::PanelStructure structure;
+    chb::SweepImage sweep[2];  // [0] forward (lower), [1] backward (upper)
 };
 
 namespace {
@@ -53,6 +59,23 @@ int guarded(Fn &&fn) {
 
 void check_dtype(int dtype) {
     if (dtype != CHB_F32 && dtype != CHB_F64) throw std::invalid_argument("dtype must be CHB_F32 or CHB_F64");
+}
+
+void fill_factor(chb::HostFactor &L, int n, int64_t nnz_l, const int32_t *l_colptr, const int32_t *l_rowidx,
+                 const double *l_vals, const int32_t *perm) {
+    if (n < 0 || l_colptr[n] != nnz_l) throw std::invalid_argument("factor: colptr[n] != nnz");
+    L.n = n;
+    L.perm.assign(perm, perm + n);
+    L.colptr.assign(l_colptr, l_colptr + n + 1);
+    L.rowidx.assign(l_rowidx, l_rowidx + nnz_l);
+    L.vals.assign(l_vals, l_vals + nnz_l);
+    for (int c = 0; c < n; ++c) {
+        if (L.colptr[c + 1] <= L.colptr[c] || L.rowidx[L.colptr[c]] != c)
+            throw std::invalid_argument("factor: every column must start with its diagonal entry");
+        for (int e = L.colptr[c] + 1; e < L.colptr[c + 1]; ++e)
+            if (L.rowidx[e] <= L.rowidx[e - 1] || L.rowidx[e] >= n)
+                throw std::invalid_argument("factor: row indices must be strictly ascending and below n");
+    }
 }
 }  // namespace
 
@@ -122,16 +145,8 @@ CHB_API int chb_solver_create_from_factor(chb_solver **out, int dtype, int n, in
     return guarded([&] {
         check_dtype(dtype);
         if (device < 0) throw std::invalid_argument("chb_solver_create_from_factor needs a CUDA device");
-        if (l_colptr[n] != nnz_l) throw std::invalid_argument("factor: colptr[n] != nnz");
         chb::HostFactor L;
-        L.n = n;
-        L.perm.assign(perm, perm + n);
-        L.colptr.assign(l_colptr, l_colptr + n + 1);
-        L.rowidx.assign(l_rowidx, l_rowidx + nnz_l);
-        L.vals.assign(l_vals, l_vals + nnz_l);
-        for (int c = 0; c < n; ++c)
-            if (L.colptr[c + 1] <= L.colptr[c] || L.rowidx[L.colptr[c]] != c)
-                throw std::invalid_argument("factor: every column must start with its diagonal entry");
+        fill_factor(L, n, nnz_l, l_colptr, l_rowidx, l_vals, perm);
         chb_solver *s = new chb_solver();
         s->dtype = dtype;
         try {
@@ -144,14 +159,23 @@ CHB_API int chb_solver_create_from_factor(chb_solver **out, int dtype, int n, in
     });
 }
 
-CHB_API int chb_solver_create_replica(chb_solver **out, int dtype, int n, int64_t nnz_l, int n_levels_lower,
-                                      int n_levels_upper, int device) {
+CHB_API int chb_solver_image_shape(const chb_solver *s, int64_t *shape, int cap) {
+    return guarded([&] {
+        chb::GpuSolver *g = s->gpu();
+        if (!g) throw std::invalid_argument("CPU-mode solvers have no device image.");
+        if (cap < chb::ImageShape::kWords) throw std::invalid_argument("shape buffer too small");
+        g->shape().to_words(shape);
+    });
+}
+
+CHB_API int chb_solver_create_replica(chb_solver **out, int dtype, const int64_t *shape, int n_words, int device) {
     return guarded([&] {
         check_dtype(dtype);
+        if (n_words < chb::ImageShape::kWords) throw std::invalid_argument("image shape too short");
         chb_solver *s = new chb_solver();
         s->dtype = dtype;
         try {
-            s->bare = new chb::GpuSolver(device, dtype == CHB_F32 ? 4 : 8, n, nnz_l, n_levels_lower, n_levels_upper);
+            s->bare = new chb::GpuSolver(device, dtype == CHB_F32 ? 4 : 8, chb::ImageShape::from_words(shape));
         } catch (...) {
             delete s;
             throw;
@@ -197,8 +221,11 @@ CHB_API int chb_solver_is_cpu(const chb_solver *s) { return s->is_cpu() ? 1 : 0;
 CHB_API int chb_solver_info(const chb_solver *s, int64_t *out, int cap) {
     chb::GpuSolver *g = s->gpu();
     if (!g) return 0;
+    const chb::SweepDev &f = g->sweep_image(false), &b = g->sweep_image(true);
     const int64_t v[] = {g->n(), g->nnz(), g->triangle(true).n_levels, g->triangle(false).n_levels, s->dtype,
-                         g->device(), g->last_grid(), g->launches_per_solve()};
+                         g->device(), g->last_grid(), g->launches_per_solve(),
+                         f.n_tasks, (int64_t) f.slab_bytes, f.n_slots, f.n_task_levels, f.n_stored_values,
+                         b.n_tasks, (int64_t) b.slab_bytes, b.n_slots, b.n_task_levels, b.n_stored_values};
     int m = (int) (sizeof(v) / sizeof(v[0]));
     if (cap < m) m = cap;
     std::memcpy(out, v, sizeof(int64_t) * (size_t) m);
@@ -209,7 +236,7 @@ CHB_API int chb_solver_get_analysis(const chb_solver *s, int lower, int32_t *lev
     return guarded([&] {
         chb::GpuSolver *g = s->gpu();
         if (!g) throw std::invalid_argument("CPU-mode solvers have no GPU analysis.");
-        const chb::TriangleDev &t = g->triangle(lower != 0);
+        const chb::TriangleAnalysis &t = g->triangle(lower != 0);
         if (t.level_of_row.empty()) throw std::runtime_error("analysis products are not kept on replicas");
         std::memcpy(level_of_row, t.level_of_row.data(), sizeof(int32_t) * (size_t) g->n());
         std::memcpy(order, t.order_host.data(), sizeof(int32_t) * (size_t) g->n());
@@ -267,3 +294,38 @@ CHB_API int chb_solver_image_buffer(const chb_solver *s, int index, const char *
         *bytes = img[index].bytes;
     });
 }
+
+CHB_API int chb_schedule_create(chb_schedule **out, int dtype, int n, int64_t nnz_l, const int32_t *l_colptr,
+                                const int32_t *l_rowidx, const double *l_vals, const int32_t *perm, int exact_order) {
+    return guarded([&] {
+        check_dtype(dtype);
+        chb::HostFactor L;
+        fill_factor(L, n, nnz_l, l_colptr, l_rowidx, l_vals, perm);
+        chb::ScheduleOptions opt = chb::schedule_options_from_env();
+        if (exact_order >= 0) opt.exact_order = exact_order != 0;
+        chb_schedule *s = new chb_schedule();
+        try {
+            chb::build_panel_structure(L, &s->structure);
+            for (int upper = 0; upper < 2; ++upper)
+                chb::build_sweep_image(L, s->structure, dtype == CHB_F32 ? 4 : 8, upper != 0, opt, &s->sweep[upper]);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+    });
+}
+CHB_API int chb_schedule_sweep(const chb_schedule *s, int upper, const void **slab, const void **tasks,
+                               const int32_t **order, int64_t *info, int cap) {
+    const chb::SweepImage &img = s->sweep[upper ? 1 : 0];
+    *slab = img.slab.data();
+    *tasks = img.tasks.data();
+    *order = img.order.data();
+    const int64_t v[] = {(int64_t) img.tasks.size(), (int64_t) img.slab.size(), img.page_bytes, img.n_slots, img.n_levels,
+                         img.n_values, img.n_stored_values, img.n_blocks, s->structure.n_panels, s->structure.n_supernodes};
+    int m = (int) (sizeof(v) / sizeof(v[0]));
+    if (cap < m) m = cap;
+    std::memcpy(info, v, sizeof(int64_t) * (size_t) m);
+    return m;
+}
+CHB_API void chb_schedule_destroy(chb_schedule *s) { delete s; }

@@ -2,8 +2,12 @@
 #include "gpu_solver.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <stdexcept>
+#include <thread>
+#include <type_traits>
 
 #include "kernel_args.h"
 
@@ -11,7 +15,10 @@ namespace chb {
 
 namespace {
 
-constexpr int kBlock = 256;  // threads per CTA of the persistent sweeps (8 warps)
+constexpr int kAnalysisBlock = 256;  // threads per CTA of the analysis kernel
+constexpr int kSweepBlock = 128;     // threads per CTA of the sweeps (4 independent warps; sweep.cuh)
+constexpr int kSweepStages = 3;      // pages in flight per warp (sweep.cuh: kStages)
+constexpr int kFuncAttrMaxDynamicSharedSize = 8;  // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES
 
 void *dev_alloc(size_t bytes) {
     void *p = nullptr;
@@ -52,59 +59,87 @@ void bucket_rows_by_level(const std::vector<int> &level_of_row, int n_levels, st
     for (int r = 0; r < n; ++r) order[cursor[level_of_row[r]]++] = r;
 }
 
+// Pattern of the CSR form of a lower-triangular CSC operand (rows sorted by column, diagonal last).
+void csc_to_csr_pattern(int n, const std::vector<int> &colptr, const std::vector<int> &rowidx, std::vector<int> &rowptr,
+                        std::vector<int> &colidx) {
+    const size_t nnz = (size_t) colptr[n];
+    rowptr.assign(n + 1, 0);
+    for (size_t p = 0; p < nnz; ++p) rowptr[rowidx[p] + 1]++;
+    std::partial_sum(rowptr.begin(), rowptr.end(), rowptr.begin());
+    colidx.resize(nnz);
+    std::vector<int> cursor(rowptr.begin(), rowptr.end() - 1);
+    for (int c = 0; c < n; ++c)
+        for (int p = colptr[c]; p < colptr[c + 1]; ++p) colidx[cursor[rowidx[p]]++] = c;
+}
+
+size_t sweep_smem_bytes(int elem) {
+    return (size_t) (kSweepBlock / 32) * kSweepStages * (size_t) page_bytes_for(elem) + (size_t) (kSweepBlock / 32) * kSweepStages * 8;
+}
+
 }  // namespace
 
-void GpuSolver::allocate_image() {
-    m_perm = dev_alloc(sizeof(int) * (size_t) m_n);
-    for (TriangleDev *t : {&m_lower, &m_upper}) {
-        t->rowptr = dev_alloc(sizeof(int) * (size_t) (m_n + 1));
-        t->colidx = dev_alloc(sizeof(int) * (size_t) m_nnz);
-        t->vals = dev_alloc((size_t) m_elem * (size_t) m_nnz);
-        t->order = dev_alloc(sizeof(int) * (size_t) m_n);
+void ImageShape::to_words(int64_t *w) const {
+    w[0] = n, w[1] = nnz;
+    for (int u = 0; u < 2; ++u) {
+        w[2 + u] = n_tasks[u], w[4 + u] = (int64_t) slab_bytes[u], w[6 + u] = n_slots[u], w[8 + u] = n_task_levels[u];
+        w[10 + u] = n_levels[u];
     }
 }
-
-void GpuSolver::allocate_scratch() {
-    m_ready = dev_alloc(sizeof(int) * (size_t) m_n);
-    m_counters = dev_alloc(sizeof(int) * 8);
-    cuda_check(cuMemsetD32Async(m_ready, 0, (size_t) m_n, nullptr));
-    cuda_check(cuMemsetD32Async(m_counters, 0, 8, nullptr));
-}
-
-void GpuSolver::upload_triangle(TriangleDev &t, const std::vector<int> &ptr, const std::vector<int> &idx,
-                                const std::vector<double> &vals) {
-    h2d(t.rowptr, ptr.data(), sizeof(int) * ptr.size());
-    h2d(t.colidx, idx.data(), sizeof(int) * idx.size());
-    if (m_elem == 8) {
-        h2d(t.vals, vals.data(), sizeof(double) * vals.size());
-        sync0();
-    } else {
-        std::vector<float> narrow(vals.size());
-        for (size_t i = 0; i < vals.size(); ++i) narrow[i] = (float) vals[i];
-        h2d(t.vals, narrow.data(), sizeof(float) * narrow.size());
-        sync0();  // `narrow` dies here
+ImageShape ImageShape::from_words(const int64_t *w) {
+    ImageShape s;
+    s.n = w[0], s.nnz = w[1];
+    for (int u = 0; u < 2; ++u) {
+        s.n_tasks[u] = w[2 + u], s.slab_bytes[u] = w[4 + u], s.n_slots[u] = w[6 + u], s.n_task_levels[u] = w[8 + u];
+        s.n_levels[u] = w[10 + u];
     }
+    return s;
 }
 
-void GpuSolver::analyze(TriangleDev &t, bool lower) {
+void GpuSolver::allocate_sweep(SweepDev &s) {
+    s.slab = dev_alloc(s.slab_bytes);
+    s.tasks = dev_alloc(sizeof(SweepTask) * (size_t) s.n_tasks);
+    s.order = dev_alloc(sizeof(int) * (size_t) s.n_tasks);
+    s.done = dev_alloc(sizeof(int) * (size_t) s.n_tasks);
+    cuda_check(cuMemsetD32Async(s.done, 0, (size_t) std::max(s.n_tasks, 1), nullptr));
+}
+
+void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
+    static_assert(sizeof(SweepTask) == sizeof(TaskDesc), "host and device task descriptors must match");
+    d.n_tasks = (int) img.tasks.size();
+    d.slab_bytes = img.slab.size();
+    d.n_slots = img.n_slots;
+    d.n_task_levels = img.n_levels;
+    d.n_stored_values = img.n_stored_values;
+    allocate_sweep(d);
+    h2d(d.slab, img.slab.data(), img.slab.size());
+    h2d(d.tasks, img.tasks.data(), sizeof(TaskDesc) * img.tasks.size());
+    h2d(d.order, img.order.data(), sizeof(int32_t) * img.order.size());
+    sync0();
+}
+
+void GpuSolver::analyze(TriangleAnalysis &t, const std::vector<int> &ptr, const std::vector<int> &idx, bool lower) {
     int *counters = (int *) m_counters;
+    void *rowptr_d = dev_alloc(sizeof(int) * ptr.size());
+    void *colidx_d = dev_alloc(sizeof(int) * idx.size());
     void *level_d = dev_alloc(sizeof(int) * (size_t) m_n);
+    h2d(rowptr_d, ptr.data(), sizeof(int) * ptr.size());
+    h2d(colidx_d, idx.data(), sizeof(int) * idx.size());
     cuda_check(cuMemsetD8Async(level_d, 0xff, sizeof(int) * (size_t) m_n, nullptr));  // all -1
     cuda_check(cuMemsetD32Async(counters + 2, 0, 2, nullptr));
 
     AnalysisArgs args;
     args.n = m_n;
     args.descending = lower ? 0 : 1;
-    args.rowptr = (const int *) t.rowptr;
-    args.colidx = (const int *) t.colidx;
+    args.rowptr = (const int *) rowptr_d;
+    args.colidx = (const int *) colidx_d;
     args.level = (int *) level_d;
     args.max_level = counters + 3;
     args.ticket = counters + 2;
     CUfunction fn = kernel(m_dev, "chb_analysis");
     if (!fn) throw std::runtime_error(driver_error_text());
-    const int grid = std::max(1, max_resident_blocks(m_dev, fn, kBlock, 0));
+    const int grid = std::max(1, max_resident_blocks(m_dev, fn, kAnalysisBlock, 0));
     void *params[] = {&args};
-    cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, kBlock, 1, 1, 0, nullptr, params));
+    cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, kAnalysisBlock, 1, 1, 0, nullptr, params));
 
     t.level_of_row.resize(m_n);
     int max_level = 0;
@@ -112,43 +147,73 @@ void GpuSolver::analyze(TriangleDev &t, bool lower) {
     d2h(&max_level, counters + 3, sizeof(int));
     sync0();
     dev_free(level_d);
+    dev_free(rowptr_d);
+    dev_free(colidx_d);
     t.n_levels = max_level + 1;
     for (int r = 0; r < m_n; ++r)
         if (t.level_of_row[r] < 0 || t.level_of_row[r] > max_level)
             throw std::runtime_error("level analysis produced an out-of-range level (GPU kernel failure)");
     bucket_rows_by_level(t.level_of_row, t.n_levels, t.order_host);
-    h2d(t.order, t.order_host.data(), sizeof(int) * (size_t) m_n);
-    sync0();
 }
 
 GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     : m_dev(require_device(device)), m_elem(elem_size), m_n(L.n), m_nnz(L.nnz()) {
     ContextGuard guard(m_dev);
-    allocate_image();
-    allocate_scratch();
+    m_counters = dev_alloc(sizeof(int) * 8);
+    cuda_check(cuMemsetD32Async(m_counters, 0, 8, nullptr));
     m_perm_host = L.perm;
-    h2d(m_perm, L.perm.data(), sizeof(int) * (size_t) m_n);
-    {
-        // CSR of L (diagonal last per row): the forward operand.
-        std::vector<int> rowptr, colidx;
-        std::vector<double> rvals;
-        csc_to_csr(L.n, L.colptr, L.rowidx, L.vals, rowptr, colidx, rvals);
-        upload_triangle(m_lower, rowptr, colidx, rvals);
+
+    // Host: lay the factor out as the two sweep images (one thread each) while the device runs the
+    // level analysis of both triangles.
+    const ScheduleOptions opt = schedule_options_from_env();
+    PanelStructure structure;
+    build_panel_structure(L, &structure);
+    SweepImage img[2];
+    std::exception_ptr errors[2];
+    std::thread builders[2];
+    for (int u = 0; u < 2; ++u)
+        builders[u] = std::thread([&, u] {
+            try {
+                build_sweep_image(L, structure, m_elem, u == 1, opt, &img[u]);
+            } catch (...) {
+                errors[u] = std::current_exception();
+            }
+        });
+    try {
+        {
+            std::vector<int> rowptr, colidx;  // CSR of L (diagonal last per row): the forward operand
+            csc_to_csr_pattern(L.n, L.colptr, L.rowidx, rowptr, colidx);
+            analyze(m_lower, rowptr, colidx, true);
+        }
+        analyze(m_upper, L.colptr, L.rowidx, false);  // CSC of L == CSR of L' (diagonal first per row)
+    } catch (...) {
+        for (auto &t : builders) t.join();
+        throw;
     }
-    // CSC of L == CSR of L' (diagonal first per row): the backward operand.
-    upload_triangle(m_upper, L.colptr, L.rowidx, L.vals);
-    analyze(m_lower, true);
-    analyze(m_upper, false);
+    for (auto &t : builders) t.join();
+    for (int u = 0; u < 2; ++u)
+        if (errors[u]) std::rethrow_exception(errors[u]);
+    for (int u = 0; u < 2; ++u) {
+        upload_sweep(m_sweep[u], img[u]);
+        img[u] = SweepImage();
+    }
     if (cuda_first_error() != CUDA_SUCCESS) throw std::runtime_error(driver_error_text());
 }
 
-GpuSolver::GpuSolver(int device, int elem_size, int n, int64_t nnz, int n_levels_lower, int n_levels_upper)
-    : m_dev(require_device(device)), m_elem(elem_size), m_n(n), m_nnz(nnz) {
+GpuSolver::GpuSolver(int device, int elem_size, const ImageShape &shape)
+    : m_dev(require_device(device)), m_elem(elem_size), m_n((int) shape.n), m_nnz(shape.nnz) {
     ContextGuard guard(m_dev);
-    allocate_image();
-    allocate_scratch();
-    m_lower.n_levels = n_levels_lower;
-    m_upper.n_levels = n_levels_upper;
+    m_counters = dev_alloc(sizeof(int) * 8);
+    cuda_check(cuMemsetD32Async(m_counters, 0, 8, nullptr));
+    for (int u = 0; u < 2; ++u) {
+        m_sweep[u].n_tasks = (int) shape.n_tasks[u];
+        m_sweep[u].slab_bytes = (uint64_t) shape.slab_bytes[u];
+        m_sweep[u].n_slots = (int) shape.n_slots[u];
+        m_sweep[u].n_task_levels = (int) shape.n_task_levels[u];
+        allocate_sweep(m_sweep[u]);
+    }
+    m_lower.n_levels = (int) shape.n_levels[0];
+    m_upper.n_levels = (int) shape.n_levels[1];
     sync0();
     if (cuda_first_error() != CUDA_SUCCESS) throw std::runtime_error(driver_error_text());
 }
@@ -156,89 +221,94 @@ GpuSolver::GpuSolver(int device, int elem_size, int n, int64_t nnz, int n_levels
 GpuSolver::~GpuSolver() {
     ContextGuard guard(m_dev);
     sync0();
-    dev_free(m_perm);
-    for (TriangleDev *t : {&m_lower, &m_upper}) {
-        dev_free(t->rowptr);
-        dev_free(t->colidx);
-        dev_free(t->vals);
-        dev_free(t->order);
+    for (SweepDev &s : m_sweep) {
+        dev_free(s.slab);
+        dev_free(s.tasks);
+        dev_free(s.order);
+        dev_free(s.done);
     }
-    dev_free(m_ready);
     dev_free(m_counters);
     dev_free(m_tmp);
+    dev_free(m_scratch);
     dev_free(m_stage_b);
     dev_free(m_stage_x);
 }
 
-std::vector<ImageBuffer> GpuSolver::image() const {
-    const size_t ni = sizeof(int) * (size_t) m_n, zi = sizeof(int) * (size_t) m_nnz;
-    const size_t zv = (size_t) m_elem * (size_t) m_nnz;
-    return {
-        {"perm", m_perm, ni},
-        {"lower.rowptr", m_lower.rowptr, ni + sizeof(int)},
-        {"lower.colidx", m_lower.colidx, zi},
-        {"lower.vals", m_lower.vals, zv},
-        {"lower.order", m_lower.order, ni},
-        {"upper.rowptr", m_upper.rowptr, ni + sizeof(int)},
-        {"upper.colidx", m_upper.colidx, zi},
-        {"upper.vals", m_upper.vals, zv},
-        {"upper.order", m_upper.order, ni},
-    };
+ImageShape GpuSolver::shape() const {
+    ImageShape s;
+    s.n = m_n, s.nnz = m_nnz;
+    for (int u = 0; u < 2; ++u) {
+        s.n_tasks[u] = m_sweep[u].n_tasks;
+        s.slab_bytes[u] = (int64_t) m_sweep[u].slab_bytes;
+        s.n_slots[u] = m_sweep[u].n_slots;
+        s.n_task_levels[u] = m_sweep[u].n_task_levels;
+    }
+    s.n_levels[0] = m_lower.n_levels;
+    s.n_levels[1] = m_upper.n_levels;
+    return s;
 }
 
-template <typename Float>
-static void fill_args(SolveArgs<Float> &a, int n, int k, bool upper, int epoch, const TriangleDev &t, void *ready,
-                      int *ticket, int *ticket_next, void *tmp, const void *src, void *dst, const void *perm) {
-    a.n = n;
-    a.k = k;
-    a.upper = upper ? 1 : 0;
-    a.epoch = epoch;
-    a.order = (const int *) t.order;
-    a.rowptr = (const int *) t.rowptr;
-    a.colidx = (const int *) t.colidx;
-    a.vals = (const Float *) t.vals;
-    a.ready = (int *) ready;
-    a.ticket = ticket;
-    a.ticket_next = ticket_next;
-    a.tmp = (Float *) tmp;
-    a.src = (const Float *) src;
-    a.dst = (Float *) dst;
-    a.perm = (const int *) perm;
+std::vector<ImageBuffer> GpuSolver::image() const {
+    std::vector<ImageBuffer> out;
+    static const char *names[2][3] = {{"lower.slab", "lower.tasks", "lower.order"}, {"upper.slab", "upper.tasks", "upper.order"}};
+    for (int u = 0; u < 2; ++u) {
+        const SweepDev &s = m_sweep[u];
+        out.push_back({names[u][0], s.slab, (size_t) s.slab_bytes});
+        out.push_back({names[u][1], s.tasks, sizeof(SweepTask) * (size_t) s.n_tasks});
+        out.push_back({names[u][2], s.order, sizeof(int) * (size_t) s.n_tasks});
+    }
+    return out;
 }
 
 void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
     char name[64];
-    const char *ty = m_elem == 4 ? "f32" : "f64";
-    if (k <= 8) {
-        const int kmax = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8;
-        snprintf(name, sizeof name, "chb_solve_narrow_%s_%d", ty, kmax);
-    } else {
-        snprintf(name, sizeof name, "chb_solve_wide_%s_%d", ty, (k + 31) / 32);
-    }
+    snprintf(name, sizeof name, "chb_sweep_%s_%d_%s", m_elem == 4 ? "f32" : "f64", (k + 31) / 32, upper ? "upper" : "lower");
     CUfunction fn = kernel(m_dev, name);
     if (!fn) throw std::runtime_error(driver_error_text());
+    const size_t smem = sweep_smem_bytes(m_elem);
+    cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
 
-    m_epoch += 1;
     int *counters = (int *) m_counters;
     int *ticket = counters + (m_sweeps & 1), *ticket_next = counters + ((m_sweeps + 1) & 1);
     m_sweeps += 1;
-    const TriangleDev &t = upper ? m_upper : m_lower;
+    const SweepDev &s = m_sweep[upper ? 1 : 0];
 
-    SolveArgs<float> a32;
-    SolveArgs<double> a64;
+    const char *flags_env = std::getenv("CHB_SWEEP_FLAGS");  // tuning knob, see sweep.cuh wait_for()
+    const int sweep_flags = flags_env ? std::atoi(flags_env) : 0;
+    auto fill = [&](auto &a) {
+        using A = std::remove_reference_t<decltype(a)>;
+        using Float = std::remove_pointer_t<decltype(A::tmp)>;
+        a.n_tasks = s.n_tasks;
+        a.k = k;
+        a.epoch = m_epoch;
+        a.reserved = sweep_flags;
+        a.slab = (const unsigned char *) s.slab;
+        a.tasks = (const SweepTask *) s.tasks;
+        a.order = (const int *) s.order;
+        a.done = (int *) s.done;
+        a.ticket = ticket;
+        a.ticket_next = ticket_next;
+        a.tmp = (Float *) m_tmp;
+        a.src = (const Float *) src;
+        a.dst = (Float *) dst;
+        a.scratch = (Float *) m_scratch;
+    };
+    SweepArgs<float> a32;
+    SweepArgs<double> a64;
     void *params[1];
     if (m_elem == 4) {
-        fill_args(a32, m_n, k, upper, m_epoch, t, m_ready, ticket, ticket_next, m_tmp, src, dst, m_perm);
+        fill(a32);
         params[0] = &a32;
     } else {
-        fill_args(a64, m_n, k, upper, m_epoch, t, m_ready, ticket, ticket_next, m_tmp, src, dst, m_perm);
+        fill(a64);
         params[0] = &a64;
     }
-    const int warps_per_block = kBlock / 32;
-    const int needed = (m_n + warps_per_block - 1) / warps_per_block;
-    const int grid = std::max(1, std::min(needed, max_resident_blocks(m_dev, fn, kBlock, 0)));
+    const int warps_per_block = kSweepBlock / 32;
+    const int needed = (s.n_tasks + warps_per_block - 1) / warps_per_block;
+    int grid = std::max(1, std::min(needed, max_resident_blocks(m_dev, fn, kSweepBlock, smem)));
+    if (const char *cap = std::getenv("CHB_SWEEP_CTAS_PER_SM")) grid = std::max(1, std::min(grid, std::atoi(cap) * m_dev->sm_count));
     m_last_grid = grid;
-    cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, kBlock, 1, 1, 0, nullptr, params));
+    cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, kSweepBlock, 1, 1, (unsigned) smem, nullptr, params));
 }
 
 void GpuSolver::solve(int k, const void *b, void *x) {
@@ -249,9 +319,13 @@ void GpuSolver::solve(int k, const void *b, void *x) {
     ContextGuard guard(m_dev);
     if (k != m_k) {
         dev_free(m_tmp);
+        dev_free(m_scratch);
         m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) k);
+        const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
+        m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) k);
         m_k = k;
     }
+    m_epoch += 1;
     sweep(false, k, b, nullptr);  // tmp = L^-1 P b
     sweep(true, k, nullptr, x);   // x = P' L^-T tmp
 }

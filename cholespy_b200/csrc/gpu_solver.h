@@ -10,18 +10,28 @@
 
 #include "cuda_driver.h"
 #include "factor_host.h"
+#include "panel_schedule.h"
 
 namespace chb {
 
-// One triangular CSR operand in HBM plus its level schedule.
-struct TriangleDev {
-    void *rowptr = nullptr;  // int32[n+1]
-    void *colidx = nullptr;  // int32[Z]
-    void *vals = nullptr;    // Float[Z]
-    void *order = nullptr;   // int32[n]: row ids grouped by level, ascending inside a level
+// Level-set analysis products of one triangle (the reference's level_ind / levels arrays).
+struct TriangleAnalysis {
     int n_levels = 0;
-    std::vector<int> level_of_row;  // host copy of the analysis result (bit-exact parity target)
-    std::vector<int> order_host;
+    std::vector<int> level_of_row;  // bit-exact parity target
+    std::vector<int> order_host;    // row ids grouped by level, ascending inside a level
+};
+
+// One sweep's image in HBM (see panel_schedule.h).
+struct SweepDev {
+    void *slab = nullptr;    // record stream
+    void *tasks = nullptr;   // SweepTask[n_tasks]
+    void *order = nullptr;   // int32[n_tasks]: ticket -> task
+    void *done = nullptr;    // int32[n_tasks]: epoch flags (scratch, not part of the image)
+    int n_tasks = 0;
+    uint64_t slab_bytes = 0;
+    int n_slots = 0;
+    int n_task_levels = 0;
+    int64_t n_stored_values = 0;
 };
 
 struct ImageBuffer {
@@ -30,14 +40,25 @@ struct ImageBuffer {
     size_t bytes;
 };
 
+// Everything a replica needs to allocate an image of the same shape.
+struct ImageShape {
+    int64_t n = 0, nnz = 0;
+    int64_t n_tasks[2] = {0, 0}, slab_bytes[2] = {0, 0}, n_slots[2] = {0, 0}, n_task_levels[2] = {0, 0};
+    int64_t n_levels[2] = {0, 0};  // reference level counts (lower, upper)
+    static constexpr int kWords = 12;
+    void to_words(int64_t *w) const;
+    static ImageShape from_words(const int64_t *w);
+};
+
 class GpuSolver {
 public:
-    // Uploads L (both orientations, values cast to `elem_size` bytes on the host like the
-    // reference, src/cholesky_solver.cpp:255-271), runs the level analysis of both triangles.
+    // Runs the level analysis of both triangles on the device, lays L out as the panel image
+    // (values cast to `elem_size` bytes on the host like the reference,
+    // src/cholesky_solver.cpp:255-271) and uploads it.
     GpuSolver(int device, int elem_size, const HostFactor &L);
     // Allocates an image of the given shape without contents (to be filled by a broadcast from a
-    // peer's image, then adopt_levels()).  Used for multi-GPU replication.
-    GpuSolver(int device, int elem_size, int n, int64_t nnz, int n_levels_lower, int n_levels_upper);
+    // peer's image).  Used for multi-GPU replication.
+    GpuSolver(int device, int elem_size, const ImageShape &shape);
     ~GpuSolver();
 
     GpuSolver(const GpuSolver &) = delete;
@@ -53,20 +74,20 @@ public:
     int64_t nnz() const { return m_nnz; }
     int elem_size() const { return m_elem; }
     int device() const { return m_dev->ordinal; }
-    const TriangleDev &triangle(bool lower) const { return lower ? m_lower : m_upper; }
+    const TriangleAnalysis &triangle(bool lower) const { return lower ? m_lower : m_upper; }
     const std::vector<int> &perm_host() const { return m_perm_host; }
     int last_grid() const { return m_last_grid; }
     int launches_per_solve() const { return 2; }
+    const SweepDev &sweep_image(bool upper) const { return m_sweep[upper ? 1 : 0]; }
+    ImageShape shape() const;
 
-    // Replicable device image: everything a peer needs to solve (factor both ways, schedule, perm).
+    // Replicable device image: everything a peer needs to solve.
     std::vector<ImageBuffer> image() const;
 
 private:
-    void allocate_image();
-    void allocate_scratch();
-    void upload_triangle(TriangleDev &t, const std::vector<int> &ptr, const std::vector<int> &idx,
-                         const std::vector<double> &vals);
-    void analyze(TriangleDev &t, bool lower);
+    void allocate_sweep(SweepDev &s);
+    void analyze(TriangleAnalysis &t, const std::vector<int> &ptr, const std::vector<int> &idx, bool lower);
+    void upload_sweep(SweepDev &d, const SweepImage &img);
     void sweep(bool upper, int k, const void *src, void *dst);
 
     DeviceState *m_dev = nullptr;
@@ -78,13 +99,13 @@ private:
     int m_sweeps = 0;
     int m_last_grid = 0;
 
-    void *m_perm = nullptr;
-    TriangleDev m_lower, m_upper;
+    TriangleAnalysis m_lower, m_upper;
     std::vector<int> m_perm_host;
+    SweepDev m_sweep[2];        // [0] forward (L), [1] backward (L')
 
-    void *m_ready = nullptr;    // int32[n] epoch flags
     void *m_counters = nullptr; // int32[8]: [0,1] sweep tickets, [2] analysis ticket, [3] analysis max level
     void *m_tmp = nullptr;      // Float[n*k]
+    void *m_scratch = nullptr;  // Float[max n_slots * 16 * k]: parked partial tiles
     void *m_stage_b = nullptr, *m_stage_x = nullptr;  // device staging for solve_host
     size_t m_stage_bytes = 0;
 };

@@ -15,24 +15,29 @@ struct AnalysisArgs {
     int *ticket;
 };
 
-// One triangular sweep (kernels.cu: chb_solve_*).
+// One panel sweep (kernels.cu: chb_sweep_*).  See panel_schedule.h for the slab/record format.
+struct SweepTask {
+    unsigned long long offset;  // byte offset of the task's slab
+    unsigned int bytes;
+    unsigned int level;
+};
+
 template <typename Float>
-struct SolveArgs {
-    int n;
+struct SweepArgs {
+    int n_tasks;
     int k;
-    int upper;
     int epoch;
-    const int *order;    // row ids in level order
-    const int *rowptr;
-    const int *colidx;
-    const Float *vals;
-    int *ready;          // per-row epoch flags
-    int *ticket;         // this sweep's ticket counter
-    int *ticket_next;    // the other counter: cleared here for the next sweep
-    Float *tmp;          // (n, k) work vector in permuted order
-    const Float *src;    // lower: user's b
-    Float *dst;          // upper: user's x
-    const int *perm;
+    int reserved;
+    const unsigned char *slab;
+    const SweepTask *tasks;
+    const int *order;     // ticket -> task id (dependencies first)
+    int *done;            // per-task epoch flags
+    int *ticket;          // this sweep's ticket counter
+    int *ticket_next;     // the other sweep's counter: cleared here
+    Float *tmp;           // (n, k) work vector in permuted order
+    const Float *src;     // forward: user's b
+    Float *dst;           // backward: user's x
+    Float *scratch;       // n_slots tiles of 16 x k
 };
 
 }  // namespace chb

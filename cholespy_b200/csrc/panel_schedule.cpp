@@ -1,0 +1,452 @@
+// Panel / block / task schedule of the factor for the sm_100a sweep kernels.  See panel_schedule.h.
+#include "panel_schedule.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+namespace chb {
+
+namespace {
+
+inline size_t round16(size_t b) { return (b + 15) & ~size_t(15); }
+inline int popc16(uint32_t m) { return __builtin_popcount(m); }
+inline int span16(uint32_t m) { return m ? 32 - __builtin_clz(m) : 0; }  // highest set bit + 1
+
+// Appends records to the image, keeping every record inside one page of its task's slab.
+class SlabWriter {
+public:
+    SlabWriter(std::vector<uint8_t> &buf, int page, int elem) : m_buf(buf), m_page((size_t) page), m_elem(elem) {}
+    void begin_task() { m_task_start = m_buf.size(); }
+    size_t size() const { return m_buf.size(); }
+
+    // Reserves a zero-filled record; returns the byte offset of its payload.
+    size_t record(uint32_t type, int32_t a, uint32_t b, uint32_t c, size_t payload_bytes) {
+        const size_t len = 16 + round16(payload_bytes);
+        if (len > m_page) throw std::logic_error("panel schedule: record larger than a page");
+        const size_t in_page = (m_buf.size() - m_task_start) % m_page;
+        if (in_page + len > m_page) header(REC_NOP, 0, 0, 0, m_page - in_page);
+        const size_t off = m_buf.size();
+        header(type, a, b, c, len);
+        return off + 16;
+    }
+    void put_value(size_t payload_off, size_t index, double v) {
+        if (m_elem == 4) {
+            const float f = (float) v;  // host-side cast, as reference src/cholesky_solver.cpp:267-270
+            std::memcpy(&m_buf[payload_off + 4 * index], &f, 4);
+        } else {
+            std::memcpy(&m_buf[payload_off + 8 * index], &v, 8);
+        }
+    }
+    void put_int(size_t payload_off, size_t index, int32_t v) { std::memcpy(&m_buf[payload_off + 4 * index], &v, 4); }
+
+private:
+    void header(uint32_t type, int32_t a, uint32_t b, uint32_t c, size_t len) {
+        const size_t off = m_buf.size();
+        m_buf.resize(off + len);  // zero-filled
+        const uint32_t h[4] = {type | (uint32_t) (len / 16) << 8, (uint32_t) a, b, c};
+        std::memcpy(&m_buf[off], h, 16);
+    }
+    std::vector<uint8_t> &m_buf;
+    size_t m_page;
+    int m_elem;
+    size_t m_task_start = 0;
+};
+
+}  // namespace
+
+ScheduleOptions schedule_options_from_env() {
+    ScheduleOptions o;
+    auto geti = [](const char *name, int dflt) {
+        const char *v = std::getenv(name);
+        return v && *v ? std::atoi(v) : dflt;
+    };
+    o.exact_order = geti("CHB_EXACT_ORDER", 0) != 0;
+    o.group_cost = std::max(1, geti("CHB_GROUP_COST", o.group_cost));
+    o.group_panels = std::max(1, geti("CHB_GROUP_PANELS", o.group_panels));
+    o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));
+    o.chunk_cost = std::max(256, geti("CHB_CHUNK_COST", o.chunk_cost));
+    return o;
+}
+
+void build_panel_structure(const HostFactor &L, PanelStructure *out) {
+    PanelStructure &S = *out;
+    const int n = L.n;
+    const std::vector<int> &cp = L.colptr, &ri = L.rowidx;
+    S = PanelStructure();
+    S.n = n;
+    S.panel_of_row.resize(n);
+    S.c0.reserve(n / 2 + 2);
+
+    // Columns j and j+1 belong to one supernode when column j is {j, j+1} + (column j+1 minus its
+    // diagonal) -- checked entry by entry so that any lower-triangular operand is handled, not only
+    // exact Cholesky structures.
+    auto chained = [&](int j) {
+        const int64_t a = cp[j], b = cp[j + 1], e = cp[j + 2];
+        const int64_t cj = b - a, cj1 = e - b;
+        if (cj < 2 || cj - 1 != cj1 || ri[a + 1] != j + 1) return false;
+        return cj1 <= 1 || std::memcmp(&ri[a + 2], &ri[b + 1], sizeof(int) * (size_t) (cj1 - 1)) == 0;
+    };
+    int j = 0;
+    while (j < n) {
+        int e = j + 1;
+        while (e < n && chained(e - 1)) ++e;
+        S.n_supernodes += 1;
+        for (int c = j; c < e; c += kPanelWidth) {
+            const int p = (int) S.c0.size();
+            S.c0.push_back(c);
+            const int c1 = std::min(c + kPanelWidth, e);
+            for (int r = c; r < c1; ++r) S.panel_of_row[r] = p;
+        }
+        j = e;
+    }
+    S.n_panels = (int) S.c0.size();
+    S.c0.push_back(n);
+
+    const int np = S.n_panels;
+    S.rlo.resize(np);
+    S.m.resize(np);
+    S.bptr.assign(np + 1, 0);
+    for (int p = 0; p < np; ++p) {
+        const int last = S.c0[p + 1] - 1;
+        S.rlo[p] = (int64_t) cp[last] + 1;
+        S.m[p] = cp[last + 1] - cp[last] - 1;
+    }
+    S.parent.resize(np);
+    for (int p = 0; p < np; ++p) S.parent[p] = S.m[p] > 0 ? S.panel_of_row[ri[S.rlo[p]]] : -1;
+    // blocks per source panel
+    for (int p = 0; p < np; ++p) {
+        const int64_t lo = S.rlo[p];
+        const int m = S.m[p];
+        int q = 0;
+        while (q < m) {
+            const int t = S.panel_of_row[ri[lo + q]];
+            const int base = S.c0[t];
+            uint32_t mask = 0;
+            const int q0 = q;
+            while (q < m && S.panel_of_row[ri[lo + q]] == t) {
+                mask |= 1u << (ri[lo + q] - base);
+                ++q;
+            }
+            S.b_src.push_back(p);
+            S.b_tgt.push_back(t);
+            S.b_q0.push_back(q0);
+            S.b_mask.push_back((uint16_t) mask);
+        }
+        S.bptr[p + 1] = (int64_t) S.b_src.size();
+    }
+    // the same blocks bucketed by target panel (stable => ascending source panel inside a bucket)
+    const int64_t nb = (int64_t) S.b_src.size();
+    S.fptr.assign(np + 1, 0);
+    for (int64_t b = 0; b < nb; ++b) S.fptr[S.b_tgt[b] + 1] += 1;
+    for (int p = 0; p < np; ++p) S.fptr[p + 1] += S.fptr[p];
+    S.flist.resize(nb);
+    {
+        std::vector<int64_t> cursor(S.fptr.begin(), S.fptr.end() - 1);
+        for (int64_t b = 0; b < nb; ++b) S.flist[cursor[S.b_tgt[b]]++] = b;
+    }
+}
+
+namespace {
+
+struct Builder {
+    const HostFactor &L;
+    const PanelStructure &S;
+    const ScheduleOptions &opt;
+    SweepImage &img;
+    SlabWriter w;
+    const bool upper;
+    std::vector<int> task_of_panel;
+    int cur = -1;
+    uint32_t cur_level = 0;
+
+    Builder(const HostFactor &L_, const PanelStructure &S_, const ScheduleOptions &o, SweepImage &i)
+        : L(L_), S(S_), opt(o), img(i), w(i.slab, i.page_bytes, i.elem), upper(i.upper), task_of_panel(S_.n_panels, -1) {}
+
+    // -- tasks ----------------------------------------------------------------------------------
+    int open_task() {
+        cur = (int) img.tasks.size();
+        img.tasks.push_back(TaskDesc{(uint64_t) w.size(), 0u, 0u});
+        w.begin_task();
+        cur_level = 0;
+        return cur;
+    }
+    void close_task() {
+        if (cur < 0) return;
+        const uint64_t bytes = (uint64_t) w.size() - img.tasks[cur].offset;
+        if (bytes >= (1ull << 32)) throw std::logic_error("panel schedule: task slab too large");
+        img.tasks[cur].bytes = (uint32_t) bytes;
+        img.tasks[cur].level = cur_level;
+        cur = -1;
+    }
+    uint32_t wait_code(int dep_task) {
+        if (dep_task < 0) throw std::logic_error("panel schedule: dependency on an unscheduled panel");
+        if (dep_task == cur) return 0;  // produced earlier by this same warp
+        cur_level = std::max(cur_level, img.tasks[dep_task].level + 1);
+        return (uint32_t) dep_task + 1;
+    }
+
+    // -- factor access --------------------------------------------------------------------------
+    // L[R_p[q], c0(p) + j]
+    double rect(int p, int j, int q) const {
+        const int c = S.c0[p] + j, wd = S.width(p);
+        return L.vals[(size_t) L.colptr[c] + (size_t) (wd - j) + (size_t) q];
+    }
+    // L[c0(p) + i, c0(p) + j], i >= j
+    double tri(int p, int i, int j) const { return L.vals[(size_t) L.colptr[S.c0[p] + j] + (size_t) (i - j)]; }
+
+    int64_t block_cost(int64_t b) const { return (int64_t) popc16(S.b_mask[b]) * S.width(S.b_src[b]); }
+    int64_t tri_cost(int p) const {
+        const int wd = S.width(p);
+        return (int64_t) wd * (wd + 1) / 2;
+    }
+
+    // Blocks of panel P in the order this sweep consumes them.
+    void blocks_of(int P, std::vector<int64_t> &out) const {
+        out.clear();
+        if (upper) {
+            for (int64_t b = S.bptr[P + 1] - 1; b >= S.bptr[P]; --b) out.push_back(b);  // farthest owner first
+        } else {
+            for (int64_t f = S.fptr[P]; f < S.fptr[P + 1]; ++f) out.push_back(S.flist[f]);  // ascending source
+        }
+    }
+
+    // Unless the reference's summation order is requested, consume the blocks whose sources finish
+    // earliest first (by dependency level), so that a task is left with as little work as possible
+    // once its last dependency arrives.  Deterministic: a pure function of the factor's pattern.
+    void order_by_readiness(std::vector<int64_t> &blocks) const {
+        if (opt.exact_order) return;
+        auto key = [&](int64_t b) -> int64_t {
+            const int t = task_of_panel[upper ? S.b_tgt[b] : S.b_src[b]];
+            return t == cur || t < 0 ? -1 : (int64_t) img.tasks[t].level;
+        };
+        std::stable_sort(blocks.begin(), blocks.end(), [&](int64_t x, int64_t y) { return key(x) < key(y); });
+    }
+
+    // -- records --------------------------------------------------------------------------------
+    void emit_begin_rhs(int P) {
+        const int wd = S.width(P), row0 = S.c0[P];
+        if (upper) {
+            w.record(REC_BEGIN_RHS, row0, (uint32_t) wd, 0, 0);
+        } else {
+            const size_t off = w.record(REC_BEGIN_RHS, row0, (uint32_t) wd, 0, 4 * kPanelWidth);
+            for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
+        }
+    }
+    void emit_begin_zero(int P) { w.record(REC_BEGIN_ZERO, S.c0[P], (uint32_t) S.width(P), 0, 0); }
+    void emit_begin_slot(int P, int slot, int dep_task) {
+        w.record(REC_BEGIN_SLOT, S.c0[P], (uint32_t) S.width(P) | (uint32_t) slot << 8, wait_code(dep_task), 0);
+    }
+    void emit_add_slot(int slot, int dep_task) { w.record(REC_ADD_SLOT, 0, (uint32_t) slot << 8, wait_code(dep_task), 0); }
+    void emit_end_slot(int slot) { w.record(REC_END_SLOT, 0, (uint32_t) slot << 8, 0, 0); }
+
+    void emit_block(int P, int64_t b) {
+        const int p = S.b_src[b], t = S.b_tgt[b], q0 = S.b_q0[b];
+        const uint32_t rows = S.b_mask[b];
+        const int nr = popc16(rows);
+        const size_t es = (size_t) img.elem;
+        img.n_blocks += 1;
+        if (upper) {
+            // unknowns = columns of p (all wd of them); sources = rows of t present in the block,
+            // visited in DESCENDING row order (reference walks a row of L' from its end backwards)
+            const int wd = S.width(p);
+            const uint32_t tmask = (1u << wd) - 1;
+            const uint32_t wait = wait_code(task_of_panel[t]);
+            const bool thin = wd <= 3;
+            const int stride = thin ? wd : (wd + 3) & ~3;
+            const size_t off = w.record(thin ? REC_BLOCK_D1 : REC_BLOCK_D4, S.c0[t], rows | tmask << 16, wait,
+                                        es * (size_t) nr * (size_t) stride);
+            for (int s = 0; s < nr; ++s) {
+                const int q = q0 + nr - 1 - s;
+                for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) s * stride + j, rect(p, j, q));
+            }
+            img.n_values += (int64_t) nr * wd;
+            img.n_stored_values += (int64_t) nr * stride;
+        } else {
+            // unknowns = rows of t present in the block; sources = all columns of p, ascending
+            (void) P;
+            const int wd = S.width(p);
+            const uint32_t smask = (1u << wd) - 1;
+            const uint32_t wait = wait_code(task_of_panel[p]);
+            const int stride = (span16(rows) + 3) & ~3;
+            if (2 * nr >= stride) {
+                const size_t off = w.record(REC_BLOCK_D4, S.c0[p], smask | rows << 16, wait, es * (size_t) wd * (size_t) stride);
+                for (int j = 0; j < wd; ++j) {
+                    int q = q0;
+                    for (int tt = 0; tt < stride; ++tt)
+                        if (rows >> tt & 1) w.put_value(off, (size_t) j * stride + tt, rect(p, j, q++));
+                }
+                img.n_stored_values += (int64_t) wd * stride;
+            } else {
+                const size_t off = w.record(REC_BLOCK_TM, S.c0[p], smask | rows << 16, wait, es * (size_t) nr * (size_t) wd);
+                for (int r = 0; r < nr; ++r)
+                    for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) r * wd + j, rect(p, j, q0 + r));
+                img.n_stored_values += (int64_t) nr * wd;
+            }
+            img.n_values += (int64_t) nr * wd;
+        }
+    }
+
+    void emit_end_final(int P) {
+        const int wd = S.width(P), row0 = S.c0[P];
+        const size_t es = (size_t) img.elem;
+        const size_t tri_bytes = round16(es * (size_t) (wd * (wd + 1) / 2));
+        const size_t head = upper ? 4 * kPanelWidth : 0;  // backward: perm[16] first (x is scattered through it)
+        const size_t off = w.record(REC_END_FINAL, row0, (uint32_t) wd, 0, head + tri_bytes);
+        if (upper)
+            for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
+        size_t idx = 0;
+        if (!upper) {
+            for (int s = 0; s < wd; ++s)  // pivot s, then column s of the triangle below it
+                for (int t = s; t < wd; ++t) w.put_value(off + head, idx++, tri(P, t, s));
+        } else {
+            for (int s = wd - 1; s >= 0; --s) {  // pivot s, then row s of the triangle left of it
+                w.put_value(off + head, idx++, tri(P, s, s));
+                for (int t = 0; t < s; ++t) w.put_value(off + head, idx++, tri(P, s, t));
+            }
+        }
+        img.n_values += (int64_t) idx;
+        img.n_stored_values += (int64_t) idx;
+        task_of_panel[P] = cur;
+    }
+
+    // One whole panel inside the current task.
+    void emit_panel(int P, std::vector<int64_t> &blocks) {
+        order_by_readiness(blocks);
+        emit_begin_rhs(P);
+        for (int64_t b : blocks) emit_block(P, b);
+        emit_end_final(P);
+    }
+
+    // A large panel: chunk tasks + a final task.
+    void emit_split_panel(int P, std::vector<int64_t> &blocks) {
+        order_by_readiness(blocks);
+        std::vector<size_t> cut{0};  // chunk boundaries in `blocks`
+        int64_t acc = 0;
+        for (size_t i = 0; i < blocks.size(); ++i) {
+            acc += block_cost(blocks[i]);
+            if (acc >= opt.chunk_cost && i + 1 < blocks.size()) {
+                cut.push_back(i + 1);
+                acc = 0;
+            }
+        }
+        cut.push_back(blocks.size());
+        const int n_chunks = (int) cut.size() - 1;
+        std::vector<int> slot(n_chunks, -1), task(n_chunks, -1);
+        for (int c = 0; c + 1 < n_chunks; ++c) {
+            task[c] = open_task();
+            if (opt.exact_order) {
+                if (c == 0) emit_begin_rhs(P);
+                else emit_begin_slot(P, slot[c - 1], task[c - 1]);
+            } else {
+                emit_begin_zero(P);
+            }
+            for (size_t i = cut[c]; i < cut[c + 1]; ++i) emit_block(P, blocks[i]);
+            slot[c] = img.n_slots++;
+            emit_end_slot(slot[c]);
+            close_task();
+        }
+        open_task();
+        if (n_chunks == 1) {
+            emit_begin_rhs(P);
+        } else if (opt.exact_order) {
+            emit_begin_slot(P, slot[n_chunks - 2], task[n_chunks - 2]);
+        } else {
+            emit_begin_rhs(P);
+            for (int c = 0; c + 1 < n_chunks; ++c) emit_add_slot(slot[c], task[c]);
+        }
+        for (size_t i = cut[n_chunks - 1]; i < cut[n_chunks]; ++i) emit_block(P, blocks[i]);
+        emit_end_final(P);
+        close_task();
+    }
+
+    void run() {
+        const int np = S.n_panels;
+        std::vector<int64_t> blocks;
+        // Tasks of several panels are COMPLETE SUBTREES of the panel elimination tree (a contiguous
+        // index range, the factor being postordered): everything outside such a task depends on it
+        // only through its root, so fusing it adds no false dependency in either sweep.
+        std::vector<int64_t> sub_cost(np);
+        std::vector<int> sub_count(np, 1), first(np);
+        for (int P = 0; P < np; ++P) {
+            blocks_of(P, blocks);
+            int64_t cost = tri_cost(P);
+            for (int64_t b : blocks) cost += block_cost(b);
+            sub_cost[P] = cost;
+            first[P] = P;
+        }
+        std::vector<int64_t> cost(sub_cost);
+        for (int P = 0; P < np; ++P) {
+            const int q = S.parent[P];
+            if (q < 0) continue;
+            sub_cost[q] += sub_cost[P];
+            sub_count[q] += sub_count[P];
+            first[q] = std::min(first[q], first[P]);
+        }
+        std::vector<int> root_of(np);
+        for (int P = 0; P < np; ++P) root_of[P] = P;
+        for (int P = np - 1; P >= 0; --P) {
+            if (root_of[P] != P) continue;  // already inside a fused subtree
+            const bool contiguous = sub_count[P] == P - first[P] + 1;
+            if (sub_count[P] > 1 && contiguous && sub_cost[P] <= opt.group_cost && sub_count[P] <= opt.group_panels)
+                for (int q = first[P]; q < P; ++q) root_of[q] = P;
+        }
+        int i = 0;
+        while (i < np) {
+            // [lo, hi] = the next run of panels forming one task, in this sweep's processing order
+            int lo, hi;
+            if (!upper) {
+                lo = i;
+                hi = root_of[i];
+            } else {
+                hi = np - 1 - i;
+                lo = root_of[hi] == hi && sub_count[hi] == hi - first[hi] + 1 && first[hi] < hi && root_of[first[hi]] == hi ? first[hi] : hi;
+            }
+            i += hi - lo + 1;
+            if (lo == hi && cost[lo] > opt.split_cost) {
+                blocks_of(lo, blocks);
+                emit_split_panel(lo, blocks);
+                continue;
+            }
+            open_task();
+            for (int c = 0; c <= hi - lo; ++c) {
+                const int P = upper ? hi - c : lo + c;
+                blocks_of(P, blocks);
+                emit_panel(P, blocks);
+            }
+            close_task();
+        }
+    }
+};
+
+}  // namespace
+
+void build_sweep_image(const HostFactor &L, const PanelStructure &S, int elem_size, bool upper,
+                       const ScheduleOptions &opt, SweepImage *out) {
+    SweepImage &img = *out;
+    img = SweepImage();
+    img.upper = upper;
+    img.elem = elem_size;
+    img.n = L.n;
+    img.page_bytes = page_bytes_for(elem_size);
+    img.slab.reserve((size_t) ((double) L.nnz() * elem_size * 1.3) + (size_t) S.n_panels * 160 + 4096);
+    Builder b(L, S, opt, img);
+    b.run();
+
+    // ticket order: by dependency level, larger slabs first inside a level
+    const int nt = (int) img.tasks.size();
+    uint32_t max_level = 0;
+    for (const TaskDesc &t : img.tasks) max_level = std::max(max_level, t.level);
+    img.n_levels = nt ? (int) max_level + 1 : 0;
+    img.order.resize(nt);
+    std::iota(img.order.begin(), img.order.end(), 0);
+    std::stable_sort(img.order.begin(), img.order.end(), [&](int a, int c) {
+        const TaskDesc &x = img.tasks[a], &y = img.tasks[c];
+        if (x.level != y.level) return x.level < y.level;
+        return x.bytes > y.bytes;
+    });
+}
+
+}  // namespace chb

@@ -1,0 +1,114 @@
+// Host-side construction of the device image the sm_100a sweep kernels stream: the factor L re-laid
+// out as a 2-D block structure over PANELS (<= 16 consecutive columns of one supernode), grouped into
+// warp-sized TASKS with a level-ordered ticket list.
+//
+// This replaces, for the solve kernels, the plain CSR/CSC upload + per-row level list of the
+// reference (reference: src/cholesky_solver.cpp:245-288, 299-376; kernels/kernels.cu:64-202).  The
+// reference's level arrays are still computed (GpuSolver::analyze) and exported bit-exactly; the
+// panel/task schedule below is an internal product derived from the same dependency structure at
+// supernode granularity.
+//
+// Terminology
+//   panel   <= 16 consecutive columns c0..c0+w-1 of L that share one below-panel row set R (they lie
+//           in one fundamental supernode) and whose diagonal block is a dense lower triangle.
+//   block   the dense rectangle L[R ∩ rows(panel t), cols(panel p)]: "block (t, p)".
+//   tile    the w x n_rhs slab of unknowns of one panel, held in registers by one warp.
+//   task    what one warp executes for one ticket: a run of consecutive small panels, or one panel,
+//           or one chunk of the blocks of a large panel (partial sums parked in a scratch slot).
+//   slab    the byte stream of one task: 16-byte-aligned records (below), streamed through shared
+//           memory in pages by 1-D TMA bulk copies; no record straddles a page boundary.
+//
+// Forward sweep (L y = P b): task of panel t PULLS from the panels p < t it has blocks with:
+//   tile[t] = b[perm[rows(t)]] - sum_p L[rows(t), cols(p)] y[cols(p)], then the in-panel triangle.
+// Backward sweep (L' x = y): task of panel p PULLS from the panels t > p owning its rows R:
+//   tile[p] = y[cols(p)] - sum_t L[R ∩ rows(t), cols(p)]' x[R ∩ rows(t)], then the triangle.
+// In both sweeps every unknown accumulates its products in exactly the reference's order
+// (ascending columns forward, descending rows backward, fused multiply-subtract, IEEE division)
+// unless a large panel is split into PARALLEL partial sums (ScheduleOptions::exact_order = false).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "factor_host.h"
+
+namespace chb {
+
+constexpr int kPanelWidth = 16;
+
+// Record types of the slab stream.  Header = 4 x u32: {type | len16 << 8, a, b, c}; len16 = record
+// length in 16-byte units including the header.
+enum RecordType : uint32_t {
+    REC_NOP = 0,         // padding up to the next page
+    REC_BEGIN_RHS = 1,   // a = row0, b = w.  tile = rhs rows (forward: payload perm[16], gather from b; backward: tmp rows)
+    REC_BEGIN_ZERO = 2,  // a = row0, b = w.  tile = 0
+    REC_BEGIN_SLOT = 3,  // a = row0, b = w | slot << 8, c = wait + 1.  tile = scratch slot (chained partial sums)
+    REC_ADD_SLOT = 4,    // b = slot << 8, c = wait + 1.  tile += scratch slot
+    REC_BLOCK_D4 = 5,    // a = src_row0, b = smask | tmask << 16, c = wait + 1.  source-major values, target
+                         // stride = round4(highest target + 1), zero-filled where a target is absent
+    REC_BLOCK_D1 = 6,    // same header; targets are the prefix 0..nt-1 (nt <= 3), stride nt, no padding
+    REC_BLOCK_TM = 7,    // same header; target-major values [target rank][source rank], no padding
+    REC_END_FINAL = 8,   // a = row0, b = w.  payload: triangle in sweep order (+ perm[16] backward); solve, store, publish
+    REC_END_SLOT = 9,    // b = slot << 8.  park the tile in a scratch slot
+};
+
+struct ScheduleOptions {
+    int group_cost = 2048;    // a whole subtree of panels is fused into one task up to this many values
+    int group_panels = 32;    // ... and at most this many panels
+    int split_cost = 8192;    // a panel with more values than this is split into chunk tasks
+    int chunk_cost = 4096;    // values per chunk task
+    bool exact_order = false; // true: chunks are CHAINED (reference summation order kept bit for bit)
+                              // false: chunks run in parallel and are summed in a fixed order
+};
+
+struct TaskDesc {
+    uint64_t offset;  // byte offset of the task's slab in the image
+    uint32_t bytes;   // slab length (multiple of 16)
+    uint32_t level;   // dependency level (informational on the device)
+};
+
+// The panel partition and block structure shared by both sweeps.
+struct PanelStructure {
+    int n = 0;
+    int n_panels = 0;
+    std::vector<int> c0;             // n_panels + 1: first column of each panel (c0[n_panels] = n)
+    std::vector<int> panel_of_row;   // n
+    std::vector<int64_t> rlo;        // n_panels: index into L.rowidx of the panel's below-panel row list
+    std::vector<int> m;              // n_panels: length of that list
+    std::vector<int> parent;         // n_panels: panel owning the first below-panel row (-1: root)
+    // blocks enumerated per SOURCE panel p (columns), ascending target panel
+    std::vector<int64_t> bptr;       // n_panels + 1
+    std::vector<int> b_src, b_tgt;   // panel ids
+    std::vector<int> b_q0;           // offset of the block's first row inside the source panel's row list
+    std::vector<uint16_t> b_mask;    // rows of the target panel present in the block
+    // the same blocks listed per TARGET panel (stable: ascending source panel)
+    std::vector<int64_t> fptr;       // n_panels + 1
+    std::vector<int64_t> flist;      // block ids
+    int n_supernodes = 0;
+    int width(int p) const { return c0[p + 1] - c0[p]; }
+};
+
+struct SweepImage {
+    bool upper = false;
+    int elem = 4;
+    int n = 0;
+    int page_bytes = 2048;
+    std::vector<uint8_t> slab;
+    std::vector<TaskDesc> tasks;
+    std::vector<int32_t> order;      // ticket -> task id, sorted by level (dependencies first)
+    int n_slots = 0;                 // scratch tiles (kPanelWidth x n_rhs elements each)
+    int n_levels = 0;
+    int64_t n_values = 0;            // factor values referenced (== nnz(L))
+    int64_t n_stored_values = 0;     // including zero fill
+    int64_t n_blocks = 0;
+};
+
+void build_panel_structure(const HostFactor &L, PanelStructure *out);
+void build_sweep_image(const HostFactor &L, const PanelStructure &S, int elem_size, bool upper,
+                       const ScheduleOptions &opt, SweepImage *out);
+
+inline int page_bytes_for(int elem_size) { return elem_size == 8 ? 4096 : 2048; }
+// Defaults, overridable for tuning / parity runs: CHB_EXACT_ORDER=1, CHB_GROUP_COST, CHB_GROUP_PANELS,
+// CHB_SPLIT_COST, CHB_CHUNK_COST.
+ScheduleOptions schedule_options_from_env();
+
+}  // namespace chb

@@ -80,7 +80,8 @@ int chb_solver_solve_cpu(chb_solver *s, int n_rhs, const void *b, void *x);
 int chb_solver_is_cpu(const chb_solver *s);
 
 /* Introspection: out[0..] = n, nnz(L), n_levels(lower), n_levels(upper), dtype, device,
- * grid size of the last sweep, kernel launches per solve.  Returns the number of values written. */
+ * grid size of the last sweep, kernel launches per solve, then per sweep (forward, backward):
+ * n_tasks, slab bytes, scratch slots, task levels, stored values.  Returns the number of values written. */
 int chb_solver_info(const chb_solver *s, int64_t *out, int cap);
 /* Analysis products of analyze_cuda (src/cholesky_solver.cpp:341-370), for bit-exact parity checks:
  * level_of_row[n] (the reference's level_ind) and order[n] (the reference's levels array). */
@@ -96,13 +97,29 @@ int64_t chb_factor_nnz(const chb_factor *f);
 int chb_factor_export(const chb_factor *f, int32_t *perm, int32_t *l_colptr, int32_t *l_rowidx, double *l_vals);
 void chb_factor_destroy(chb_factor *f);
 
-/* Multi-GPU replication of the device image (factor both ways + level schedule + permutation):
- * build the solver on one GPU, create empty replicas of the same shape on the others, and broadcast
- * each image buffer (NCCL) from the source into the replica.  New; the reference is single-GPU. */
-int chb_solver_create_replica(chb_solver **out, int dtype, int n, int64_t nnz_l, int n_levels_lower, int n_levels_upper,
-                              int device);
+/* Multi-GPU replication of the device image (both sweep images: record slabs, task tables, ticket
+ * orders): build the solver on one GPU, read its shape, create empty replicas of the same shape on
+ * the others, and broadcast each image buffer (NCCL) from the source into the replica.  New; the
+ * reference is single-GPU.  shape = CHB_IMAGE_SHAPE_WORDS int64 words. */
+#define CHB_IMAGE_SHAPE_WORDS 12
+int chb_solver_image_shape(const chb_solver *s, int64_t *shape, int cap);
+int chb_solver_create_replica(chb_solver **out, int dtype, const int64_t *shape, int n_words, int device);
 int chb_solver_image_count(const chb_solver *s);
 int chb_solver_image_buffer(const chb_solver *s, int index, const char **name, void **dptr, uint64_t *bytes);
+
+/* Host-side export of the sweep schedule the kernels stream (csrc/panel_schedule.h): the factor re-laid
+ * out as panels / blocks / tasks with a level-ordered ticket list.  Needs no GPU; used by the CPU
+ * tests (which interpret it with oracle/panel_emulator.cpp) and for inspection.  New: the reference
+ * uploads plain CSR/CSC (src/cholesky_solver.cpp:299-376).
+ * exact_order: -1 = library default / environment, 0 = parallel partial sums, 1 = chained (reference order). */
+typedef struct chb_schedule chb_schedule;
+int chb_schedule_create(chb_schedule **out, int dtype, int n, int64_t nnz_l, const int32_t *l_colptr,
+                        const int32_t *l_rowidx, const double *l_vals, const int32_t *perm, int exact_order);
+/* info[0..9] = n_tasks, slab bytes, page bytes, n_slots, n_levels, n_values, n_stored_values, n_blocks,
+ * n_panels, n_supernodes.  tasks = array of {uint64 offset, uint32 bytes, uint32 level}. */
+int chb_schedule_sweep(const chb_schedule *s, int upper, const void **slab, const void **tasks, const int32_t **order,
+                       int64_t *info, int cap);
+void chb_schedule_destroy(chb_schedule *s);
 
 #ifdef __cplusplus
 }

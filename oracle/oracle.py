@@ -173,3 +173,62 @@ class ReferenceSolver:
             self.close()
         except Exception:
             pass
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU interpreter of the product's sweep schedule (oracle/panel_emulator.cpp).
+# --------------------------------------------------------------------------------------------------
+_EMU_SO = os.path.join(_HERE, "libpanel_emu.so")
+_emu = None
+
+
+def _load_emu():
+    global _emu
+    if _emu is None:
+        if not os.path.exists(_EMU_SO):
+            build()
+        _emu = ctypes.CDLL(_EMU_SO)
+    return _emu
+
+
+SCHEDULE_INFO_KEYS = ("n_tasks", "slab_bytes", "page_bytes", "n_slots", "n_levels", "n_values", "n_stored_values",
+                      "n_blocks", "n_panels", "n_supernodes")
+
+
+def schedule_solve(lib, l_colptr, l_rowidx, l_vals, perm, b, exact_order=-1):
+    """Builds the product's sweep schedule on the host (C ABI: chb_schedule_create) and executes it with
+    the sequential CPU interpreter.  Returns (x, info_forward, info_backward)."""
+    emu = _load_emu()
+    dt = b.dtype
+    assert dt in (np.float32, np.float64)
+    n = len(l_colptr) - 1
+    k = 1 if b.ndim == 1 else b.shape[1]
+    l_colptr = np.ascontiguousarray(l_colptr, np.int32)
+    l_rowidx = np.ascontiguousarray(l_rowidx, np.int32)
+    l_vals = np.ascontiguousarray(l_vals, np.float64)
+    perm = np.ascontiguousarray(perm, np.int32)
+    h = ctypes.c_void_p()
+    rc = lib.chb_schedule_create(ctypes.byref(h), 0 if dt == np.float32 else 1, n, len(l_rowidx), _p(l_colptr), _p(l_rowidx),
+                                 _p(l_vals), _p(perm), exact_order)
+    if rc:
+        raise RuntimeError(lib.chb_last_error().decode())
+    try:
+        b2 = np.ascontiguousarray(b.reshape(n, k))
+        tmp = np.zeros((n, k), dt)
+        x = np.zeros((n, k), dt)
+        infos = []
+        fn = emu.chb_emu_sweep_f32 if dt == np.float32 else emu.chb_emu_sweep_f64
+        for upper in (0, 1):
+            slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+            info = (ctypes.c_int64 * 10)()
+            lib.chb_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 10)
+            info = dict(zip(SCHEDULE_INFO_KEYS, list(info)))
+            infos.append(info)
+            scratch = np.zeros((max(info["n_slots"], 1), 16, k), dt)
+            rc = fn(slab, tasks, order, ctypes.c_int(info["n_tasks"]), ctypes.c_int(info["page_bytes"]), ctypes.c_int(upper),
+                    ctypes.c_int(k), _p(tmp), _p(b2), _p(x), _p(scratch))
+            if rc:
+                raise RuntimeError("schedule interpreter failed with code %d (%s sweep)" % (rc, "backward" if upper else "forward"))
+    finally:
+        lib.chb_schedule_destroy(h)
+    return x.reshape(b.shape), infos[0], infos[1]

@@ -1,0 +1,157 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into or called by the product library.
+//
+// Sequential CPU interpreter of the task/record stream that cholespy_b200's host code builds for the
+// sm_100a sweep kernels (cholespy_b200/csrc/panel_schedule.h).  It executes the tasks one at a time
+// in TICKET ORDER with the arithmetic the device kernels use (fused multiply-subtract, IEEE
+// division, same accumulation order), and fails if a task consumes something a later ticket
+// produces.  The CPU tests use it to check the schedule builder against the row-by-row oracle
+// (cholespy_oracle.c, which follows the reference kernels/kernels.cu:81-120,149-190) without a GPU.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr int W = 16;
+
+struct TaskDesc {
+    uint64_t offset;
+    uint32_t bytes;
+    uint32_t level;
+};
+
+inline float fnma(float a, float b, float c) { return __builtin_fmaf(-a, b, c); }
+inline double fnma(double a, double b, double c) { return __builtin_fma(-a, b, c); }
+inline int span16(uint32_t m) { return m ? 32 - __builtin_clz(m) : 0; }
+
+enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT };
+
+// returns 0, or a negative error code
+template <typename F>
+int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_tasks, int page, int upper, int k, F *tmp,
+        const F *b, F *x, F *scratch) {
+    std::vector<uint8_t> done((size_t) n_tasks, 0);
+    std::vector<F> acc((size_t) W * k);
+    auto waited = [&](uint32_t c) { return c == 0 || done[c - 1]; };
+    for (int ticket = 0; ticket < n_tasks; ++ticket) {
+        const int task = order[ticket];
+        const uint8_t *base = slab + tasks[task].offset;
+        const uint32_t total = tasks[task].bytes;
+        if (total % 16) return -2;
+        int row0 = -1, w = 0;
+        for (uint32_t pg = 0; pg < total; pg += (uint32_t) page) {
+            const uint32_t plen = total - pg < (uint32_t) page ? total - pg : (uint32_t) page;
+            uint32_t p = 0;
+            while (p < plen) {
+                uint32_t h[4];
+                std::memcpy(h, base + pg + p, 16);
+                const uint32_t type = h[0] & 0xff, len = (h[0] >> 8) * 16;
+                if (len < 16 || p + len > plen) return -3;  // record straddles a page
+                const uint8_t *pay = base + pg + p + 16;
+                const F *v = (const F *) pay;
+                switch (type) {
+                case NOP: break;
+                case BEGIN_RHS: {
+                    row0 = (int) h[1], w = (int) h[2];
+                    std::fill(acc.begin(), acc.end(), F(0));
+                    const int32_t *perm = (const int32_t *) pay;
+                    for (int i = 0; i < w; ++i)
+                        for (int c = 0; c < k; ++c)
+                            acc[(size_t) i * k + c] = upper ? tmp[(size_t) (row0 + i) * k + c] : b[(size_t) perm[i] * k + c];
+                } break;
+                case BEGIN_ZERO:
+                    row0 = (int) h[1], w = (int) h[2];
+                    std::fill(acc.begin(), acc.end(), F(0));
+                    break;
+                case BEGIN_SLOT: {
+                    row0 = (int) h[1], w = (int) (h[2] & 0xff);
+                    if (!waited(h[3])) return -4;
+                    const F *s = scratch + (size_t) (h[2] >> 8) * W * k;
+                    std::copy(s, s + (size_t) W * k, acc.begin());
+                } break;
+                case ADD_SLOT: {
+                    if (!waited(h[3])) return -4;
+                    const F *s = scratch + (size_t) (h[2] >> 8) * W * k;
+                    for (size_t i = 0; i < (size_t) W * k; ++i) acc[i] += s[i];
+                } break;
+                case BLOCK_D4:
+                case BLOCK_D1: {
+                    if (!waited(h[3])) return -4;
+                    const int src0 = (int) h[1];
+                    const uint32_t smask = h[2] & 0xffff, tmask = h[2] >> 16;
+                    const int stride = type == BLOCK_D4 ? (span16(tmask) + 3) & ~3 : __builtin_popcount(tmask);
+                    int r = 0;
+                    for (int bit = 0; bit < W; ++bit) {
+                        const int s = upper ? W - 1 - bit : bit;
+                        if (!(smask >> s & 1)) continue;
+                        const F *srow = tmp + (size_t) (src0 + s) * k;
+                        for (int t = 0; t < stride; ++t)
+                            for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(v[(size_t) r * stride + t], srow[c], acc[(size_t) t * k + c]);
+                        ++r;
+                    }
+                } break;
+                case BLOCK_TM: {
+                    if (!waited(h[3])) return -4;
+                    const int src0 = (int) h[1];
+                    const uint32_t smask = h[2] & 0xffff, tmask = h[2] >> 16;
+                    const int ns = __builtin_popcount(smask);
+                    int r = 0;
+                    for (int t = 0; t < W; ++t) {
+                        if (!(tmask >> t & 1)) continue;
+                        int sr = 0;
+                        for (int bit = 0; bit < W; ++bit) {
+                            const int s = upper ? W - 1 - bit : bit;
+                            if (!(smask >> s & 1)) continue;
+                            const F *srow = tmp + (size_t) (src0 + s) * k;
+                            for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(v[(size_t) r * ns + sr], srow[c], acc[(size_t) t * k + c]);
+                            ++sr;
+                        }
+                        ++r;
+                    }
+                } break;
+                case END_FINAL: {
+                    if ((int) h[1] != row0 || (int) h[2] != w) return -5;
+                    const int32_t *perm = (const int32_t *) pay;
+                    if (upper) v = (const F *) (pay + 4 * W);
+                    size_t idx = 0;
+                    for (int step = 0; step < w; ++step) {
+                        const int s = upper ? w - 1 - step : step;
+                        const F d = v[idx++];
+                        for (int c = 0; c < k; ++c) acc[(size_t) s * k + c] = acc[(size_t) s * k + c] / d;
+                        const int t0 = upper ? 0 : s + 1, t1 = upper ? s : w;
+                        for (int t = t0; t < t1; ++t) {
+                            const F l = v[idx++];
+                            for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(l, acc[(size_t) s * k + c], acc[(size_t) t * k + c]);
+                        }
+                    }
+                    for (int i = 0; i < w; ++i)
+                        for (int c = 0; c < k; ++c) {
+                            tmp[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
+                            if (upper) x[(size_t) perm[i] * k + c] = acc[(size_t) i * k + c];
+                        }
+                } break;
+                case END_SLOT: {
+                    F *s = scratch + (size_t) (h[2] >> 8) * W * k;
+                    std::copy(acc.begin(), acc.end(), s);
+                } break;
+                default: return -6;
+                }
+                p += len;
+            }
+        }
+        done[task] = 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int chb_emu_sweep_f32(const void *slab, const void *tasks, const int32_t *order, int n_tasks, int page, int upper, int k,
+                                 float *tmp, const float *b, float *x, float *scratch) {
+    return run<float>((const uint8_t *) slab, (const TaskDesc *) tasks, order, n_tasks, page, upper, k, tmp, b, x, scratch);
+}
+extern "C" int chb_emu_sweep_f64(const void *slab, const void *tasks, const int32_t *order, int n_tasks, int page, int upper, int k,
+                                 double *tmp, const double *b, double *x, double *scratch) {
+    return run<double>((const uint8_t *) slab, (const TaskDesc *) tasks, order, n_tasks, page, upper, k, tmp, b, x, scratch);
+}
