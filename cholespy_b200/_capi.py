@@ -39,6 +39,7 @@ _SIGNATURES = {
     "chb_solver_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "chb_solver_get_analysis": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
     "chb_solver_get_perm": (ctypes.c_int, [c_vp, c_vp]),
+    "chb_solver_get_trace": (ctypes.c_int64, [c_vp, ctypes.c_int, c_vp, ctypes.c_int64]),
     "chb_factorize": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_int]),
     "chb_factor_n": (ctypes.c_int, [c_vp]),
     "chb_factor_nnz": (ctypes.c_int64, [c_vp]),

@@ -243,6 +243,12 @@ CHB_API int chb_solver_get_analysis(const chb_solver *s, int lower, int32_t *lev
     });
 }
 
+CHB_API int64_t chb_solver_get_trace(chb_solver *s, int upper, uint64_t *out, int64_t cap) {
+    chb::GpuSolver *g = s->gpu();
+    if (!g) return 0;
+    return (int64_t) g->copy_trace(upper != 0, (unsigned long long *) out, (size_t) cap);
+}
+
 CHB_API int chb_solver_get_perm(const chb_solver *s, int32_t *perm) {
     return guarded([&] {
         chb::GpuSolver *g = s->gpu();
@@ -305,7 +311,7 @@ CHB_API int chb_schedule_create(chb_schedule **out, int dtype, int n, int64_t nn
         if (exact_order >= 0) opt.exact_order = exact_order != 0;
         chb_schedule *s = new chb_schedule();
         try {
-            chb::build_panel_structure(L, &s->structure);
+            chb::build_panel_structure(L, opt, &s->structure);
             for (int upper = 0; upper < 2; ++upper)
                 chb::build_sweep_image(L, s->structure, dtype == CHB_F32 ? 4 : 8, upper != 0, opt, &s->sweep[upper]);
         } catch (...) {

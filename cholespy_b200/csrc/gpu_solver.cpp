@@ -72,8 +72,14 @@ void csc_to_csr_pattern(int n, const std::vector<int> &colptr, const std::vector
         for (int p = colptr[c]; p < colptr[c + 1]; ++p) colidx[cursor[rowidx[p]]++] = c;
 }
 
-size_t sweep_smem_bytes(int elem) {
-    return (size_t) (kSweepBlock / 32) * kSweepStages * (size_t) page_bytes_for(elem) + (size_t) (kSweepBlock / 32) * kSweepStages * 8;
+int padded_rhs(int k) { return (k + 3) & ~3; }  // row stride of the work vector (whole 16-byte chunks)
+
+// Dynamic shared memory of one sweep CTA (sweep.cuh): slab rings + row rings + mbarriers.
+size_t sweep_smem_bytes(int elem, int k) {
+    const size_t warps = kSweepBlock / 32;
+    const size_t row_slots = 16;  // sweep.cuh: row_slots()
+    return warps * kSweepStages * (size_t) page_bytes_for(elem) + warps * row_slots * (size_t) padded_rhs(k) * (size_t) elem +
+           warps * kSweepStages * 8;
 }
 
 }  // namespace
@@ -101,6 +107,21 @@ void GpuSolver::allocate_sweep(SweepDev &s) {
     s.order = dev_alloc(sizeof(int) * (size_t) s.n_tasks);
     s.done = dev_alloc(sizeof(int) * (size_t) s.n_tasks);
     cuda_check(cuMemsetD32Async(s.done, 0, (size_t) std::max(s.n_tasks, 1), nullptr));
+    const char *trace = std::getenv("CHB_TRACE");
+    if (trace && std::atoi(trace) != 0) {
+        s.trace = dev_alloc(sizeof(unsigned long long) * 8 * (size_t) s.n_tasks);
+        cuda_check(cuMemsetD8Async(s.trace, 0, sizeof(unsigned long long) * 8 * (size_t) s.n_tasks, nullptr));
+    }
+}
+
+size_t GpuSolver::copy_trace(bool upper, unsigned long long *out, size_t cap) {
+    const SweepDev &s = m_sweep[upper ? 1 : 0];
+    if (!s.trace) return 0;
+    ContextGuard guard(m_dev);
+    const size_t words = std::min(cap, (size_t) 8 * (size_t) s.n_tasks);
+    d2h(out, s.trace, sizeof(unsigned long long) * words);
+    sync0();
+    return words;
 }
 
 void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
@@ -167,7 +188,7 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     // level analysis of both triangles.
     const ScheduleOptions opt = schedule_options_from_env();
     PanelStructure structure;
-    build_panel_structure(L, &structure);
+    build_panel_structure(L, opt, &structure);
     SweepImage img[2];
     std::exception_ptr errors[2];
     std::thread builders[2];
@@ -226,6 +247,7 @@ GpuSolver::~GpuSolver() {
         dev_free(s.tasks);
         dev_free(s.order);
         dev_free(s.done);
+        dev_free(s.trace);
     }
     dev_free(m_counters);
     dev_free(m_tmp);
@@ -265,7 +287,7 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
     snprintf(name, sizeof name, "chb_sweep_%s_%d_%s", m_elem == 4 ? "f32" : "f64", (k + 31) / 32, upper ? "upper" : "lower");
     CUfunction fn = kernel(m_dev, name);
     if (!fn) throw std::runtime_error(driver_error_text());
-    const size_t smem = sweep_smem_bytes(m_elem);
+    const size_t smem = sweep_smem_bytes(m_elem, k);
     cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
 
     int *counters = (int *) m_counters;
@@ -273,15 +295,13 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
     m_sweeps += 1;
     const SweepDev &s = m_sweep[upper ? 1 : 0];
 
-    const char *flags_env = std::getenv("CHB_SWEEP_FLAGS");  // tuning knob, see sweep.cuh wait_for()
-    const int sweep_flags = flags_env ? std::atoi(flags_env) : 0;
     auto fill = [&](auto &a) {
         using A = std::remove_reference_t<decltype(a)>;
         using Float = std::remove_pointer_t<decltype(A::tmp)>;
         a.n_tasks = s.n_tasks;
         a.k = k;
         a.epoch = m_epoch;
-        a.reserved = sweep_flags;
+        a.reserved = 0;
         a.slab = (const unsigned char *) s.slab;
         a.tasks = (const SweepTask *) s.tasks;
         a.order = (const int *) s.order;
@@ -292,6 +312,7 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
         a.src = (const Float *) src;
         a.dst = (Float *) dst;
         a.scratch = (Float *) m_scratch;
+        a.trace = (unsigned long long *) s.trace;
     };
     SweepArgs<float> a32;
     SweepArgs<double> a64;
@@ -320,7 +341,7 @@ void GpuSolver::solve(int k, const void *b, void *x) {
     if (k != m_k) {
         dev_free(m_tmp);
         dev_free(m_scratch);
-        m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) k);
+        m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) padded_rhs(k));
         const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
         m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) k);
         m_k = k;

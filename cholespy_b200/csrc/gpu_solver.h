@@ -27,6 +27,7 @@ struct SweepDev {
     void *tasks = nullptr;   // SweepTask[n_tasks]
     void *order = nullptr;   // int32[n_tasks]: ticket -> task
     void *done = nullptr;    // int32[n_tasks]: epoch flags (scratch, not part of the image)
+    void *trace = nullptr;   // uint64[8 * n_tasks] when CHB_TRACE=1 (debug timeline), else null
     int n_tasks = 0;
     uint64_t slab_bytes = 0;
     int n_slots = 0;
@@ -80,6 +81,8 @@ public:
     int launches_per_solve() const { return 2; }
     const SweepDev &sweep_image(bool upper) const { return m_sweep[upper ? 1 : 0]; }
     ImageShape shape() const;
+    // Debug timeline of the last solve (CHB_TRACE=1): 8 x n_tasks words, see kernel_args.h.  Returns words copied.
+    size_t copy_trace(bool upper, unsigned long long *out, size_t cap);
 
     // Replicable device image: everything a peer needs to solve.
     std::vector<ImageBuffer> image() const;

@@ -68,66 +68,84 @@ ScheduleOptions schedule_options_from_env() {
     o.group_panels = std::max(1, geti("CHB_GROUP_PANELS", o.group_panels));
     o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));
     o.chunk_cost = std::max(256, geti("CHB_CHUNK_COST", o.chunk_cost));
+    if (const char *v = std::getenv("CHB_RELAX_ALPHA")) o.relax_alpha = std::max(1.0, std::atof(v));
+    if (const char *v = std::getenv("CHB_RELAX_BETA")) o.relax_beta = std::max(0.0, std::atof(v));
     return o;
 }
 
-void build_panel_structure(const HostFactor &L, PanelStructure *out) {
+void build_panel_structure(const HostFactor &L, const ScheduleOptions &opt, PanelStructure *out) {
     PanelStructure &S = *out;
     const int n = L.n;
     const std::vector<int> &cp = L.colptr, &ri = L.rowidx;
     S = PanelStructure();
     S.n = n;
     S.panel_of_row.resize(n);
-    S.c0.reserve(n / 2 + 2);
+    S.c0.reserve(n / 4 + 2);
 
-    // Columns j and j+1 belong to one supernode when column j is {j, j+1} + (column j+1 minus its
-    // diagonal) -- checked entry by entry so that any lower-triangular operand is handled, not only
-    // exact Cholesky structures.
-    auto chained = [&](int j) {
-        const int64_t a = cp[j], b = cp[j + 1], e = cp[j + 2];
-        const int64_t cj = b - a, cj1 = e - b;
-        if (cj < 2 || cj - 1 != cj1 || ri[a + 1] != j + 1) return false;
-        return cj1 <= 1 || std::memcmp(&ri[a + 2], &ri[b + 1], sizeof(int) * (size_t) (cj1 - 1)) == 0;
-    };
-    int j = 0;
-    while (j < n) {
-        int e = j + 1;
-        while (e < n && chained(e - 1)) ++e;
-        S.n_supernodes += 1;
-        for (int c = j; c < e; c += kPanelWidth) {
-            const int p = (int) S.c0.size();
-            S.c0.push_back(c);
-            const int c1 = std::min(c + kPanelWidth, e);
-            for (int r = c; r < c1; ++r) S.panel_of_row[r] = p;
+    // Greedy RELAXED panels: consecutive columns are packed into one panel (<= 16 wide) as long as the
+    // dense layout it implies -- full triangle + (union of the columns' below-panel rows) x width,
+    // absent entries stored as explicit zeros -- stays within alpha * (true non-zeros) + beta values.
+    // Columns of one fundamental supernode have identical structure (no fill at all), so wide
+    // supernodes simply split into 16-column panels; the many 1-3 column supernodes at the bottom
+    // of the elimination tree are amalgamated, which is what keeps the number of panels, blocks
+    // and dependency hops (the latency-bound part of the sweeps) small.  Explicit zeros are
+    // bit-neutral under fused multiply-subtract, so the reference summation order is unaffected.
+    //
+    // A panel must not couple unrelated parts of the elimination tree, or it would chain sibling
+    // subtrees through false dependencies: the columns of a panel whose etree parent lies outside it
+    // ("tops") must all have the SAME parent.  Panels are therefore runs of complete sibling pieces,
+    // optionally continued up their common parent chain.
+    auto etree_parent = [&](int j) { return cp[j + 1] - cp[j] > 1 ? ri[cp[j] + 1] : -1; };
+    std::vector<int> uni, merged;
+    int a = 0;
+    while (a < n) {
+        int w = 1;
+        int64_t true_vals = cp[a + 1] - cp[a];
+        int tops_parent = etree_parent(a);
+        uni.assign(ri.begin() + cp[a] + 1, ri.begin() + cp[a + 1]);  // rows > a of the panel so far (incl. in-panel)
+        while (a + w < n && w < kPanelWidth) {
+            const int jn = a + w;
+            if (tops_parent != jn && tops_parent != etree_parent(jn)) break;  // would join unrelated subtrees
+            merged.clear();
+            std::set_union(uni.begin(), uni.end(), ri.begin() + cp[jn] + 1, ri.begin() + cp[jn + 1], std::back_inserter(merged));
+            const int64_t tv = true_vals + (cp[jn + 1] - cp[jn]);
+            const int wn = w + 1;
+            const int64_t below = (int64_t) (merged.end() - std::upper_bound(merged.begin(), merged.end(), jn));
+            const int64_t padded = (int64_t) wn * (wn + 1) / 2 + below * wn;
+            if ((double) padded > opt.relax_alpha * (double) tv + opt.relax_beta) break;
+            uni.swap(merged);
+            true_vals = tv;
+            w = wn;
+            tops_parent = etree_parent(jn);  // either all old tops were children of jn, or they are its siblings
         }
-        j = e;
+        const int p = (int) S.c0.size();
+        S.c0.push_back(a);
+        for (int r = a; r < a + w; ++r) S.panel_of_row[r] = p;
+        S.rlo.push_back((int64_t) S.rows.size());
+        const auto first_below = std::lower_bound(uni.begin(), uni.end(), a + w);
+        S.rows.insert(S.rows.end(), first_below, uni.end());
+        S.m.push_back((int) (uni.end() - first_below));
+        a += w;
     }
     S.n_panels = (int) S.c0.size();
     S.c0.push_back(n);
-
     const int np = S.n_panels;
-    S.rlo.resize(np);
-    S.m.resize(np);
     S.bptr.assign(np + 1, 0);
-    for (int p = 0; p < np; ++p) {
-        const int last = S.c0[p + 1] - 1;
-        S.rlo[p] = (int64_t) cp[last] + 1;
-        S.m[p] = cp[last + 1] - cp[last] - 1;
-    }
     S.parent.resize(np);
-    for (int p = 0; p < np; ++p) S.parent[p] = S.m[p] > 0 ? S.panel_of_row[ri[S.rlo[p]]] : -1;
+    for (int p = 0; p < np; ++p) S.parent[p] = S.m[p] > 0 ? S.panel_of_row[S.rows[S.rlo[p]]] : -1;
+    const std::vector<int> &rr = S.rows;
     // blocks per source panel
     for (int p = 0; p < np; ++p) {
         const int64_t lo = S.rlo[p];
         const int m = S.m[p];
         int q = 0;
         while (q < m) {
-            const int t = S.panel_of_row[ri[lo + q]];
+            const int t = S.panel_of_row[rr[lo + q]];
             const int base = S.c0[t];
             uint32_t mask = 0;
             const int q0 = q;
-            while (q < m && S.panel_of_row[ri[lo + q]] == t) {
-                mask |= 1u << (ri[lo + q] - base);
+            while (q < m && S.panel_of_row[rr[lo + q]] == t) {
+                mask |= 1u << (rr[lo + q] - base);
                 ++q;
             }
             S.b_src.push_back(p);
@@ -189,13 +207,38 @@ struct Builder {
     }
 
     // -- factor access --------------------------------------------------------------------------
-    // L[R_p[q], c0(p) + j]
-    double rect(int p, int j, int q) const {
-        const int c = S.c0[p] + j, wd = S.width(p);
-        return L.vals[(size_t) L.colptr[c] + (size_t) (wd - j) + (size_t) q];
+    // Dense copy of L[R_p[q0 .. q0+nr), columns of p] (absent entries = 0); returns the number present.
+    int gather_block(int p, int q0, int nr, double (&buf)[kPanelWidth][kPanelWidth]) const {
+        const int c0 = S.c0[p], wd = S.width(p);
+        const int *R = &S.rows[(size_t) S.rlo[p] + (size_t) q0];
+        int present = 0;
+        for (int j = 0; j < wd; ++j) {
+            const int c = c0 + j;
+            const int *cr = &L.rowidx[(size_t) L.colptr[c]];
+            const int len = L.colptr[c + 1] - L.colptr[c];
+            int at = (int) (std::lower_bound(cr, cr + len, R[0]) - cr);
+            for (int q = 0; q < nr; ++q) {
+                while (at < len && cr[at] < R[q]) ++at;
+                if (at < len && cr[at] == R[q]) {
+                    buf[q][j] = L.vals[(size_t) L.colptr[c] + (size_t) at];
+                    present += 1;
+                } else {
+                    buf[q][j] = 0.0;
+                }
+            }
+        }
+        return present;
     }
-    // L[c0(p) + i, c0(p) + j], i >= j
-    double tri(int p, int i, int j) const { return L.vals[(size_t) L.colptr[S.c0[p] + j] + (size_t) (i - j)]; }
+    // L[c0(p) + i, c0(p) + j], i >= j (0 if absent; `present` counts the entries that exist)
+    double tri(int p, int i, int j, int *present = nullptr) const {
+        const int c = S.c0[p] + j, row = S.c0[p] + i;
+        for (int e = L.colptr[c]; e < L.colptr[c + 1] && L.rowidx[e] <= row; ++e)
+            if (L.rowidx[e] == row) {
+                if (present) *present += 1;
+                return L.vals[(size_t) e];
+            }
+        return 0.0;
+    }
 
     int64_t block_cost(int64_t b) const { return (int64_t) popc16(S.b_mask[b]) * S.width(S.b_src[b]); }
     int64_t tri_cost(int p) const {
@@ -248,6 +291,8 @@ struct Builder {
         const int nr = popc16(rows);
         const size_t es = (size_t) img.elem;
         img.n_blocks += 1;
+        double buf[kPanelWidth][kPanelWidth];  // [row of the block][column of p]
+        img.n_values += gather_block(p, q0, nr, buf);
         if (upper) {
             // unknowns = columns of p (all wd of them); sources = rows of t present in the block,
             // visited in DESCENDING row order (reference walks a row of L' from its end backwards)
@@ -258,11 +303,8 @@ struct Builder {
             const int stride = thin ? wd : (wd + 3) & ~3;
             const size_t off = w.record(thin ? REC_BLOCK_D1 : REC_BLOCK_D4, S.c0[t], rows | tmask << 16, wait,
                                         es * (size_t) nr * (size_t) stride);
-            for (int s = 0; s < nr; ++s) {
-                const int q = q0 + nr - 1 - s;
-                for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) s * stride + j, rect(p, j, q));
-            }
-            img.n_values += (int64_t) nr * wd;
+            for (int s = 0; s < nr; ++s)
+                for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) s * stride + j, buf[nr - 1 - s][j]);
             img.n_stored_values += (int64_t) nr * stride;
         } else {
             // unknowns = rows of t present in the block; sources = all columns of p, ascending
@@ -274,22 +316,48 @@ struct Builder {
             if (2 * nr >= stride) {
                 const size_t off = w.record(REC_BLOCK_D4, S.c0[p], smask | rows << 16, wait, es * (size_t) wd * (size_t) stride);
                 for (int j = 0; j < wd; ++j) {
-                    int q = q0;
+                    int q = 0;
                     for (int tt = 0; tt < stride; ++tt)
-                        if (rows >> tt & 1) w.put_value(off, (size_t) j * stride + tt, rect(p, j, q++));
+                        if (rows >> tt & 1) w.put_value(off, (size_t) j * stride + tt, buf[q++][j]);
                 }
                 img.n_stored_values += (int64_t) wd * stride;
             } else {
                 const size_t off = w.record(REC_BLOCK_TM, S.c0[p], smask | rows << 16, wait, es * (size_t) nr * (size_t) wd);
                 for (int r = 0; r < nr; ++r)
-                    for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) r * wd + j, rect(p, j, q0 + r));
+                    for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) r * wd + j, buf[r][j]);
                 img.n_stored_values += (int64_t) nr * wd;
             }
-            img.n_values += (int64_t) nr * wd;
         }
     }
 
+    // Fast mode: the triangle as a dense wp x wp matrix (wp = 1 or round4(w)) in pivot order with
+    // RECIPROCAL pivots, so the kernel's substitution is branch-free with static shared-memory
+    // offsets and has no division on its dependency chain.  Row s = pivot s: [s][s] = 1/L[s,s],
+    // [s][t] = the multiplier of unknown t (forward: t > s, L[t,s]; backward: t < s, L[s,t]).
+    void emit_end_dense(int P) {
+        const int wd = S.width(P), row0 = S.c0[P];
+        const size_t es = (size_t) img.elem;
+        const int wp = wd == 1 ? 1 : (wd + 3) & ~3;
+        const size_t head = upper ? 4 * kPanelWidth : 0;
+        const size_t off = w.record(REC_END_DENSE, row0, (uint32_t) wd, 0, head + es * (size_t) (wp * wp));
+        if (upper)
+            for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
+        int present = 0;
+        for (int s = 0; s < wp; ++s) {
+            w.put_value(off + head, (size_t) s * wp + s, s < wd ? 1.0 / tri(P, s, s, &present) : 1.0);
+            if (s >= wd) continue;
+            if (!upper)
+                for (int t = s + 1; t < wd; ++t) w.put_value(off + head, (size_t) s * wp + t, tri(P, t, s, &present));
+            else
+                for (int t = 0; t < s; ++t) w.put_value(off + head, (size_t) s * wp + t, tri(P, s, t, &present));
+        }
+        img.n_values += present;
+        img.n_stored_values += (int64_t) wp * wp;
+        task_of_panel[P] = cur;
+    }
+
     void emit_end_final(int P) {
+        if (!opt.exact_order) return emit_end_dense(P);
         const int wd = S.width(P), row0 = S.c0[P];
         const size_t es = (size_t) img.elem;
         const size_t tri_bytes = round16(es * (size_t) (wd * (wd + 1) / 2));
@@ -298,16 +366,17 @@ struct Builder {
         if (upper)
             for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
         size_t idx = 0;
+        int present = 0;
         if (!upper) {
             for (int s = 0; s < wd; ++s)  // pivot s, then column s of the triangle below it
-                for (int t = s; t < wd; ++t) w.put_value(off + head, idx++, tri(P, t, s));
+                for (int t = s; t < wd; ++t) w.put_value(off + head, idx++, tri(P, t, s, &present));
         } else {
             for (int s = wd - 1; s >= 0; --s) {  // pivot s, then row s of the triangle left of it
-                w.put_value(off + head, idx++, tri(P, s, s));
-                for (int t = 0; t < s; ++t) w.put_value(off + head, idx++, tri(P, s, t));
+                w.put_value(off + head, idx++, tri(P, s, s, &present));
+                for (int t = 0; t < s; ++t) w.put_value(off + head, idx++, tri(P, s, t, &present));
             }
         }
-        img.n_values += (int64_t) idx;
+        img.n_values += present;
         img.n_stored_values += (int64_t) idx;
         task_of_panel[P] = cur;
     }

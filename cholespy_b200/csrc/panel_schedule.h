@@ -9,8 +9,10 @@
 // supernode granularity.
 //
 // Terminology
-//   panel   <= 16 consecutive columns c0..c0+w-1 of L that share one below-panel row set R (they lie
-//           in one fundamental supernode) and whose diagonal block is a dense lower triangle.
+//   panel   <= 16 consecutive columns c0..c0+w-1 of L treated as one dense block column: a dense lower
+//           triangle on the diagonal and one below-panel row set R (the union over its columns).
+//           Columns of a fundamental supernode share R exactly; small neighbouring supernodes are
+//           amalgamated ("relaxed"), their absent entries stored as explicit zeros.
 //   block   the dense rectangle L[R ∩ rows(panel t), cols(panel p)]: "block (t, p)".
 //   tile    the w x n_rhs slab of unknowns of one panel, held in registers by one warp.
 //   task    what one warp executes for one ticket: a run of consecutive small panels, or one panel,
@@ -24,7 +26,9 @@
 //   tile[p] = y[cols(p)] - sum_t L[R ∩ rows(t), cols(p)]' x[R ∩ rows(t)], then the triangle.
 // In both sweeps every unknown accumulates its products in exactly the reference's order
 // (ascending columns forward, descending rows backward, fused multiply-subtract, IEEE division)
-// unless a large panel is split into PARALLEL partial sums (ScheduleOptions::exact_order = false).
+// when ScheduleOptions::exact_order is set.  The default (fast) schedule instead splits large panels
+// into PARALLEL partial sums, consumes blocks in order of readiness and multiplies by reciprocal
+// pivots: deterministic, same operation count, different rounding (within the stated tolerance).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -49,6 +53,8 @@ enum RecordType : uint32_t {
     REC_BLOCK_TM = 7,    // same header; target-major values [target rank][source rank], no padding
     REC_END_FINAL = 8,   // a = row0, b = w.  payload: triangle in sweep order (+ perm[16] backward); solve, store, publish
     REC_END_SLOT = 9,    // b = slot << 8.  park the tile in a scratch slot
+    REC_END_DENSE = 10,  // a = row0, b = w.  like END_FINAL with the triangle as a dense wp x wp matrix (wp = 1 or
+                         // round4(w)) holding RECIPROCAL pivots: multiply instead of divide (fast mode only)
 };
 
 struct ScheduleOptions {
@@ -56,6 +62,8 @@ struct ScheduleOptions {
     int group_panels = 32;    // ... and at most this many panels
     int split_cost = 8192;    // a panel with more values than this is split into chunk tasks
     int chunk_cost = 4096;    // values per chunk task
+    double relax_alpha = 1.5; // relaxed panels: stored values <= alpha * non-zeros + beta (1.0 / 0: no fill)
+    double relax_beta = 32.0;
     bool exact_order = false; // true: chunks are CHAINED (reference summation order kept bit for bit)
                               // false: chunks run in parallel and are summed in a fixed order
 };
@@ -72,7 +80,8 @@ struct PanelStructure {
     int n_panels = 0;
     std::vector<int> c0;             // n_panels + 1: first column of each panel (c0[n_panels] = n)
     std::vector<int> panel_of_row;   // n
-    std::vector<int64_t> rlo;        // n_panels: index into L.rowidx of the panel's below-panel row list
+    std::vector<int> rows;           // concatenated below-panel row lists (sorted union over the panel's columns)
+    std::vector<int64_t> rlo;        // n_panels: offset of the panel's list in `rows`
     std::vector<int> m;              // n_panels: length of that list
     std::vector<int> parent;         // n_panels: panel owning the first below-panel row (-1: root)
     // blocks enumerated per SOURCE panel p (columns), ascending target panel
@@ -102,13 +111,13 @@ struct SweepImage {
     int64_t n_blocks = 0;
 };
 
-void build_panel_structure(const HostFactor &L, PanelStructure *out);
+void build_panel_structure(const HostFactor &L, const ScheduleOptions &opt, PanelStructure *out);
 void build_sweep_image(const HostFactor &L, const PanelStructure &S, int elem_size, bool upper,
                        const ScheduleOptions &opt, SweepImage *out);
 
 inline int page_bytes_for(int elem_size) { return elem_size == 8 ? 4096 : 2048; }
 // Defaults, overridable for tuning / parity runs: CHB_EXACT_ORDER=1, CHB_GROUP_COST, CHB_GROUP_PANELS,
-// CHB_SPLIT_COST, CHB_CHUNK_COST.
+// CHB_SPLIT_COST, CHB_CHUNK_COST, CHB_RELAX_ALPHA, CHB_RELAX_BETA.
 ScheduleOptions schedule_options_from_env();
 
 }  // namespace chb

@@ -15,9 +15,16 @@
 //   * the tile (<= 16 rows x n_rhs) of the panel being solved lives in registers: lane l owns RHS
 //     columns l, l+32, ... (NV per lane), so every gathered row of already-solved unknowns is one
 //     coalesced 128-byte line per column group and is reused for up to 16 x NV FMAs;
-//   * factor values are broadcast from shared memory (LDS.128 for the dense block layout);
+//   * consecutive block records are processed in BATCHES: lane i fetches the ready flag of the
+//     i-th block of the batch (one L2 round trip for up to 32 flags), then the source rows of every
+//     ready block are copied into a per-warp shared-memory row ring with cp.async.cg (one more
+//     round trip for up to kRowSlots rows, none of them through registers), then the arithmetic
+//     runs out of shared memory: factor values broadcast (LDS.128 for the dense block layout),
+//     source rows read conflict-free;
 //   * dependencies: one epoch-valued ready flag per TASK (ld.acquire.gpu / st.release.gpu); flags
 //     are never cleared (the epoch is the solve counter);
+//   * the work vector `tmp` has its row stride padded to 4 elements so every row is a whole number
+//     of 16-byte cp.async chunks;
 //   * P is fused into the forward tile load, P' into the backward tile store.
 #pragma once
 #include <cstdint>
@@ -35,7 +42,9 @@ constexpr int kWarpsPerCta = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
 
 enum : uint32_t { REC_NOP = 0, REC_BEGIN_RHS, REC_BEGIN_ZERO, REC_BEGIN_SLOT, REC_ADD_SLOT, REC_BLOCK_D4, REC_BLOCK_D1,
-                  REC_BLOCK_TM, REC_END_FINAL, REC_END_SLOT };
+                  REC_BLOCK_TM, REC_END_FINAL, REC_END_SLOT, REC_END_DENSE };
+
+__host__ __device__ constexpr int row_slots(int) { return 16; }  // rows staged per batch (one full block)
 
 template <typename F> struct PageOf { static constexpr int bytes = sizeof(F) == 8 ? 4096 : 2048; };
 
@@ -71,13 +80,19 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ int ld_relaxed_gpu(const int *p) {
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void st_release_gpu(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ float fnma(float a, float b, float c) { return fmaf(-a, b, c); }
 __device__ __forceinline__ double fnma(double a, double b, double c) { return fma(-a, b, c); }
@@ -110,50 +125,6 @@ __device__ __forceinline__ void put_row(Tile<F, NV> &T, int t, const F (&r)[NV])
 #undef SWEEP_PUT
 }
 
-template <typename F, int NV>
-__device__ __forceinline__ void load_row_cg(F (&r)[NV], const F *row, int lane, int k) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) r[v] = lane + 32 * v < k ? __ldcg(row + lane + 32 * v) : F(0);
-}
-
-template <typename F> struct GroupOf { static constexpr int rows = sizeof(F) == 8 ? 2 : 4; };  // source rows fetched together
-
-// Calls body(x, rank) once per source row of `mask` in sweep order (ascending rows forward,
-// descending backward); rows are fetched kGroup at a time, one group ahead of the arithmetic.
-template <typename F, int NV, bool UPPER, typename Body>
-__device__ __forceinline__ void for_sources(uint32_t mask, const F *rows, int lane, int k, Body &&body) {
-    constexpr int kGroup = GroupOf<F>::rows;
-    F xa[kGroup][NV], xb[kGroup][NV];
-    auto fetch = [&](F(&x)[kGroup][NV]) {
-        int cnt = 0;
-#pragma unroll
-        for (int g = 0; g < kGroup; ++g)
-            if (mask) {
-                const int s = UPPER ? 31 - __clz(mask) : __ffs(mask) - 1;
-                mask &= ~(1u << s);
-                load_row_cg<F, NV>(x[g], rows + (size_t) s * k, lane, k);
-                cnt = g + 1;
-            }
-        return cnt;
-    };
-    auto apply = [&](const F(&x)[kGroup][NV], int cnt, int rank) {
-#pragma unroll
-        for (int g = 0; g < kGroup; ++g)
-            if (g < cnt) body(x[g], rank + g);
-    };
-    int rank = 0;
-    int na = fetch(xa);
-    while (na) {
-        const int nb = fetch(xb);
-        apply(xa, na, rank);
-        rank += na;
-        if (!nb) break;
-        na = fetch(xa);
-        apply(xb, nb, rank);
-        rank += nb;
-    }
-}
-
 template <typename F> struct Vec4;
 template <> struct Vec4<float> {
     float x[4];
@@ -170,17 +141,65 @@ template <> struct Vec4<double> {
     }
 };
 
+// One staged source row (shared memory) -> this lane's columns.
+template <typename F, int NV>
+__device__ __forceinline__ void read_row(F (&x)[NV], const F *row, int lane, int k) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) x[v] = lane + 32 * v < k ? row[lane + 32 * v] : F(0);
+}
+
+// Substitution with the panel's triangle given as a dense WP x WP matrix with reciprocal pivots
+// (REC_END_DENSE): fully static, one row of WP values per pivot from shared memory.
+template <typename F, int NV, bool UPPER, int WP>
+__device__ __forceinline__ void tri_dense(Tile<F, NV> &T, const F *m) {
+#pragma unroll
+    for (int step = 0; step < WP; ++step) {
+        const int s = UPPER ? WP - 1 - step : step;
+        F row[WP];
+        if constexpr (WP == 1) {
+            row[0] = m[0];
+        } else {
+#pragma unroll
+            for (int q = 0; q < WP / 4; ++q) {
+                const Vec4<F> vv = Vec4<F>::load(m + s * WP + 4 * q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) row[4 * q + j] = vv.x[j];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) T.a[s][v] = T.a[s][v] * row[s];
+#pragma unroll
+        for (int t = UPPER ? 0 : s + 1; t < (UPPER ? s : WP); ++t)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) T.a[t][v] = fnma(row[t], T.a[s][v], T.a[t][v]);
+    }
+}
+
+__device__ __forceinline__ bool is_block(uint32_t type) { return type >= REC_BLOCK_D4 && type <= REC_BLOCK_TM; }
+__device__ __forceinline__ int next_source(uint32_t &mask, bool upper) {
+    const int s = upper ? 31 - __clz(mask) : __ffs(mask) - 1;
+    mask &= ~(1u << s);
+    return s;
+}
+
 // ---- the worker ----------------------------------------------------------------------------------
+// Dynamic shared memory per CTA: [warp][kStages][PAGE] slab rings, [warp][kRowSlots][kp] row rings,
+// [warp][kStages] mbarriers; kp = k rounded up to 4 elements.
 template <typename F, int NV, bool UPPER>
 __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
     constexpr int PAGE = PageOf<F>::bytes;
+    constexpr int kRowSlots = row_slots((int) sizeof(F));
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char *ring = smem_raw + (size_t) warp * kStages * PAGE;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t) kWarpsPerCta * kStages * PAGE) + warp * kStages;
     const int k = a.k;
+    const int kp = (k + 3) & ~3;   // row stride of tmp and of the staged rows
     const int epoch = a.epoch;
+    unsigned char *ring = smem_raw + (size_t) warp * kStages * PAGE;
+    F *rowring = reinterpret_cast<F *>(smem_raw + (size_t) kWarpsPerCta * kStages * PAGE) + (size_t) warp * kRowSlots * kp;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t) kWarpsPerCta * kStages * PAGE +
+                                                  (size_t) kWarpsPerCta * kRowSlots * kp * sizeof(F)) + warp * kStages;
+    const int chunks_per_row = kp * (int) sizeof(F) / 16;
 
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket_next = 0;
     if (lane == 0) {
@@ -193,39 +212,19 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
 
     uint32_t pages_issued = 0, pages_consumed = 0;  // running counts over all tasks of this warp (warp-uniform)
     Tile<F, NV> T;
-    uint32_t last_ready = 0;  // wait code most recently confirmed
+    long long wait_cycles = 0;  // tracing only
+    int cur_task = 0;
 
-    uint32_t peek_code = 0;   // flag fetched ahead of the block that needs it
-    int peek_value = 0;
-
+    // Blocks until the task behind a wait code has published (acquire).
     auto wait_for = [&](uint32_t code) {
-        if (code == 0 || code == last_ready) return;
-        if (code == peek_code && peek_value == epoch) {
-            last_ready = code;
-            return;
-        }
+        if (code == 0) return;
         const int *flag = a.done + (code - 1);
-        // a.reserved (tuning): 0 = acquire-load spin; 1 = acquire first, relaxed spin, acquire last;
-        // 2 = relaxed spin only (every mutable datum is read with an L2-coherent ld.cg behind the
-        // control dependency on the flag); +4 = back off with nanosleep while spinning
-        const int mode = a.reserved & 3;
-        if (mode == 0) {
-            while (ld_acquire_gpu(flag) != epoch) {
-                if (a.reserved & 4) __nanosleep(40);
-            }
-        } else if (mode == 1) {
-            if (ld_acquire_gpu(flag) != epoch) {
-                while (ld_relaxed_gpu(flag) != epoch) {
-                    if (a.reserved & 4) __nanosleep(40);
-                }
-                (void) ld_acquire_gpu(flag);
-            }
-        } else {
-            while (ld_relaxed_gpu(flag) != epoch) {
-                if (a.reserved & 4) __nanosleep(40);
-            }
+        const long long c0 = a.trace ? clock64() : 0;
+        while (ld_acquire_gpu(flag) != epoch) {}
+        if (a.trace) {
+            wait_cycles += clock64() - c0;
+            if (lane == 0) a.trace[8 * (size_t) cur_task + 4] = global_ns();  // last blocking wait returned
         }
-        last_ready = code;
     };
 
     for (;;) {
@@ -234,7 +233,12 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
         ticket = __shfl_sync(kFullMask, ticket, 0);
         if (ticket >= a.n_tasks) break;
         const int task = a.order[ticket];
+        cur_task = task;
         const SweepTask td = a.tasks[task];
+        if (a.trace && lane == 0) {
+            a.trace[8 * (size_t) task] = global_ns();
+            wait_cycles = 0;
+        }
         const unsigned char *base = a.slab + td.offset;
         const uint32_t total = td.bytes;
         const uint32_t n_pages = (total + PAGE - 1) / PAGE;
@@ -252,9 +256,83 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
         }
 
         int row0 = 0, w = 0;
+        auto store_tile = [&](const int *perm) {
+            if (a.trace && lane == 0) a.trace[8 * (size_t) task + 6] = global_ns();  // triangle done
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                if (i < w) {
+                    F *row = a.tmp + (size_t) (row0 + i) * kp;
+                    F *out = UPPER ? a.dst + (size_t) perm[i] * k : nullptr;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        if (lane + 32 * v < k) {
+                            __stcg(row + lane + 32 * v, T.a[i][v]);
+                            if (UPPER) out[lane + 32 * v] = T.a[i][v];
+                        }
+                }
+            }
+        };
+
+        // One block record, its source rows already staged at `xrow` (consecutive slots, sweep order).
+        auto run_block = [&](uint32_t type, const uint4 &h, const unsigned char *pay, const F *xrow) {
+            const uint32_t tmask = h.z >> 16, smask = h.z & 0xffff;
+            const F *val = reinterpret_cast<const F *>(pay);
+            const int ns = __popc(smask);
+            if (type == REC_BLOCK_D4) {
+                const int stride = (32 - __clz(tmask) + 3) & ~3;
+                for (int r = 0; r < ns; ++r) {
+                    F x[NV];
+                    read_row<F, NV>(x, xrow + (size_t) r * kp, lane, k);
+                    const F *vr = val + r * stride;
+#pragma unroll
+                    for (int t4 = 0; t4 < W / 4; ++t4) {
+                        if (t4 * 4 < stride) {
+                            const Vec4<F> vv = Vec4<F>::load(vr + t4 * 4);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) T.a[t4 * 4 + j][v] = fnma(vv.x[j], x[v], T.a[t4 * 4 + j][v]);
+                        }
+                    }
+                }
+            } else if (type == REC_BLOCK_D1) {
+                const int nt = __popc(tmask);
+                for (int r = 0; r < ns; ++r) {
+                    F x[NV];
+                    read_row<F, NV>(x, xrow + (size_t) r * kp, lane, k);
+                    const F *vr = val + r * nt;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+                        if (t < nt) {
+                            const F l = vr[t];
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) T.a[t][v] = fnma(l, x[v], T.a[t][v]);
+                        }
+                }
+            } else {  // REC_BLOCK_TM: target-major, arbitrary target set
+                uint32_t tm = tmask;
+                while (tm) {
+                    const int t = __ffs(tm) - 1;
+                    tm &= tm - 1;
+                    F acc[NV];
+                    get_row<F, NV>(T, t, acc);
+                    for (int r = 0; r < ns; ++r) {
+                        F x[NV];
+                        read_row<F, NV>(x, xrow + (size_t) r * kp, lane, k);
+                        const F l = val[r];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) acc[v] = fnma(l, x[v], acc[v]);
+                    }
+                    val += ns;
+                    put_row<F, NV>(T, t, acc);
+                }
+            }
+        };
+
         for (uint32_t pg = 0; pg < n_pages; ++pg) {
             const uint32_t stage = pages_consumed % kStages;
             mbar_wait(bars + stage, (pages_consumed / kStages) & 1);
+            if (a.trace && lane == 0 && pg == 0) a.trace[8 * (size_t) task + 1] = global_ns();
             const unsigned char *p = ring + (size_t) stage * PAGE;
             const unsigned char *pend = p + min((uint32_t) PAGE, total - pg * PAGE);
             while (p < pend) {
@@ -262,95 +340,71 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
                 const uint32_t type = h.x & 0xff;
                 const uint32_t len = (h.x >> 8) * 16;
                 const unsigned char *pay = p + 16;
+                if (is_block(type)) {
+                    // ---- batch: consecutive block records whose source rows fit the row ring ----
+                    int n_blocks = 0, n_rows = 0;
+                    uint32_t my_code = 0;
+                    for (const unsigned char *q = p; q < pend && n_blocks < 32;) {
+                        const uint4 hq = *reinterpret_cast<const uint4 *>(q);
+                        if (!is_block(hq.x & 0xff)) break;
+                        const int ns = __popc(hq.z & 0xffff);
+                        if (n_rows + ns > kRowSlots) break;
+                        if (lane == n_blocks) my_code = hq.w;
+                        n_rows += ns;
+                        n_blocks += 1;
+                        q += (hq.x >> 8) * 16;
+                    }
+                    // one ready flag per lane; blocks before the first unfinished dependency go now
+                    bool ready = true;
+                    if (my_code != 0) ready = ld_acquire_gpu(a.done + (my_code - 1)) == epoch;
+                    const unsigned pending = __ballot_sync(kFullMask, !ready);
+                    int n_go = pending ? __ffs(pending) - 1 : n_blocks;
+                    if (n_go == 0) {
+                        wait_for(h.w);
+                        n_go = 1;
+                    }
+                    // stage the source rows of those blocks
+                    {
+                        const unsigned char *q = p;
+                        int slot = 0;
+                        for (int i = 0; i < n_go; ++i) {
+                            const uint4 hq = *reinterpret_cast<const uint4 *>(q);
+                            uint32_t sm = hq.z & 0xffff;
+                            const F *rows = a.tmp + (size_t) (int) hq.y * kp;
+                            while (sm) {
+                                const int s = next_source(sm, UPPER);
+                                const unsigned char *src = reinterpret_cast<const unsigned char *>(rows + (size_t) s * kp);
+                                unsigned char *dst = reinterpret_cast<unsigned char *>(rowring + (size_t) slot * kp);
+                                for (int c = lane; c < chunks_per_row; c += 32) cp_async_16(dst + 16 * c, src + 16 * c);
+                                slot += 1;
+                            }
+                            q += (hq.x >> 8) * 16;
+                        }
+                        cp_async_wait_all();
+                        __syncwarp();
+                    }
+                    // arithmetic out of shared memory
+                    {
+                        int slot = 0;
+                        for (int i = 0; i < n_go; ++i) {
+                            const uint4 hq = *reinterpret_cast<const uint4 *>(p);
+                            run_block(hq.x & 0xff, hq, p + 16, rowring + (size_t) slot * kp);
+                            slot += __popc(hq.z & 0xffff);
+                            p += (hq.x >> 8) * 16;
+                        }
+                    }
+                    __syncwarp();  // the row ring is reused by the next batch
+                    continue;
+                }
                 p += len;
-                if (type == REC_BLOCK_D4 || type == REC_BLOCK_D1 || type == REC_BLOCK_TM) {
-                    wait_for(h.w);
-                    // start fetching the ready flag of the next block while this one is processed
-                    if (p < pend) {
-                        const uint4 hn = *reinterpret_cast<const uint4 *>(p);
-                        const uint32_t tn = hn.x & 0xff;
-                        if ((tn == REC_BLOCK_D4 || tn == REC_BLOCK_D1 || tn == REC_BLOCK_TM) && hn.w != 0 && hn.w != last_ready) {
-                            peek_code = hn.w;
-                            peek_value = ld_acquire_gpu(a.done + (hn.w - 1));
-                        }
-                    }
-                    const uint32_t tmask = h.z >> 16, smask = h.z & 0xffff;
-                    const F *val = reinterpret_cast<const F *>(pay);
-                    const F *rows = a.tmp + (size_t) (int) h.y * k;
-                    if (type == REC_BLOCK_D4) {
-                        const int stride = (32 - __clz(tmask) + 3) & ~3;
-                        for_sources<F, NV, UPPER>(smask, rows, lane, k, [&](const F(&x)[NV], int rank) {
-                            const F *vr = val + rank * stride;
-#pragma unroll
-                            for (int t4 = 0; t4 < W / 4; ++t4) {
-                                if (t4 * 4 < stride) {
-                                    const Vec4<F> vv = Vec4<F>::load(vr + t4 * 4);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                                        for (int v = 0; v < NV; ++v) T.a[t4 * 4 + j][v] = fnma(vv.x[j], x[v], T.a[t4 * 4 + j][v]);
-                                }
-                            }
-                        });
-                    } else if (type == REC_BLOCK_D1) {
-                        const int nt = __popc(tmask);
-                        for_sources<F, NV, UPPER>(smask, rows, lane, k, [&](const F(&x)[NV], int rank) {
-                            const F *vr = val + rank * nt;
-#pragma unroll
-                            for (int t = 0; t < 3; ++t)
-                                if (t < nt) {
-                                    const F l = vr[t];
-#pragma unroll
-                                    for (int v = 0; v < NV; ++v) T.a[t][v] = fnma(l, x[v], T.a[t][v]);
-                                }
-                        });
-                    } else {
-                        // target-major: sources are fetched kGroup rows at a time and applied to every
-                        // target of the block before the next group (same per-target order as row by row)
-                        constexpr int kGroup = GroupOf<F>::rows;
-                        const int ns = __popc(smask);
-                        uint32_t sm = smask;
-                        int s_rank = 0;
-                        while (sm) {
-                            F xs[kGroup][NV];
-                            int cnt = 0;
-#pragma unroll
-                            for (int g = 0; g < kGroup; ++g)
-                                if (sm) {
-                                    const int s = UPPER ? 31 - __clz(sm) : __ffs(sm) - 1;
-                                    sm &= ~(1u << s);
-                                    load_row_cg<F, NV>(xs[g], rows + (size_t) s * k, lane, k);
-                                    cnt = g + 1;
-                                }
-                            uint32_t tm = tmask;
-                            int t_rank = 0;
-                            while (tm) {
-                                const int t = __ffs(tm) - 1;
-                                tm &= tm - 1;
-                                F r[NV];
-                                get_row<F, NV>(T, t, r);
-                                const F *vr = val + t_rank * ns + s_rank;
-#pragma unroll
-                                for (int g = 0; g < kGroup; ++g)
-                                    if (g < cnt) {
-                                        const F l = vr[g];
-#pragma unroll
-                                        for (int v = 0; v < NV; ++v) r[v] = fnma(l, xs[g][v], r[v]);
-                                    }
-                                put_row<F, NV>(T, t, r);
-                                ++t_rank;
-                            }
-                            s_rank += cnt;
-                        }
-                    }
-                } else if (type == REC_BEGIN_RHS) {
+                if (type == REC_BEGIN_RHS) {
                     row0 = (int) h.y;
                     w = (int) h.z;
                     const int *perm = reinterpret_cast<const int *>(pay);
 #pragma unroll
                     for (int i = 0; i < W; ++i) {
                         const F *row = nullptr;
-                        if (i < w) row = UPPER ? a.tmp + (size_t) (row0 + i) * k : a.src + (size_t) perm[i] * k;
+                        if (i < w) row = UPPER ? a.tmp + (size_t) (row0 + i) * kp : a.src + (size_t) perm[i] * k;
 #pragma unroll
                         for (int v = 0; v < NV; ++v) {
                             F val = F(0);
@@ -358,39 +412,40 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
                             T.a[i][v] = val;
                         }
                     }
+                } else if (type == REC_END_DENSE) {
+                    if (a.trace && lane == 0) a.trace[8 * (size_t) task + 5] = global_ns();  // blocks done
+                    const int *perm = reinterpret_cast<const int *>(pay);
+                    const F *m = reinterpret_cast<const F *>(pay + (UPPER ? 4 * W : 0));
+                    if (w == 1) tri_dense<F, NV, UPPER, 1>(T, m);
+                    else if (w <= 4) tri_dense<F, NV, UPPER, 4>(T, m);
+                    else if (w <= 8) tri_dense<F, NV, UPPER, 8>(T, m);
+                    else if (w <= 12) tri_dense<F, NV, UPPER, 12>(T, m);
+                    else tri_dense<F, NV, UPPER, 16>(T, m);
+                    store_tile(perm);
                 } else if (type == REC_END_FINAL) {
+                    // reference-order substitution: packed triangle, IEEE division (exact_order schedules)
+                    if (a.trace && lane == 0) a.trace[8 * (size_t) task + 5] = global_ns();
                     const int *perm = reinterpret_cast<const int *>(pay);
                     const F *tv = reinterpret_cast<const F *>(pay + (UPPER ? 4 * W : 0));
+#pragma unroll 1
+                    for (int step = 0; step < w; ++step) {
+                        const int s = UPPER ? w - 1 - step : step;
+                        const F d = *tv++;
+                        F x[NV];
+                        get_row<F, NV>(T, s, x);
 #pragma unroll
-                    for (int step = 0; step < W; ++step) {
-                        const int s = UPPER ? W - 1 - step : step;
-                        if (s < w) {
-                            const F d = *tv++;
+                        for (int v = 0; v < NV; ++v) x[v] = x[v] / d;
+                        put_row<F, NV>(T, s, x);
 #pragma unroll
-                            for (int v = 0; v < NV; ++v) T.a[s][v] = T.a[s][v] / d;
+                        for (int t = 0; t < W; ++t) {
+                            if (UPPER ? t < s : (t > s && t < w)) {
+                                const F l = *tv++;
 #pragma unroll
-                            for (int t = UPPER ? 0 : s + 1; t < (UPPER ? s : W); ++t) {
-                                if (UPPER || t < w) {
-                                    const F l = *tv++;
-#pragma unroll
-                                    for (int v = 0; v < NV; ++v) T.a[t][v] = fnma(l, T.a[s][v], T.a[t][v]);
-                                }
+                                for (int v = 0; v < NV; ++v) T.a[t][v] = fnma(l, x[v], T.a[t][v]);
                             }
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < W; ++i) {
-                        if (i < w) {
-                            F *row = a.tmp + (size_t) (row0 + i) * k;
-                            F *out = UPPER ? a.dst + (size_t) perm[i] * k : nullptr;
-#pragma unroll
-                            for (int v = 0; v < NV; ++v)
-                                if (lane + 32 * v < k) {
-                                    __stcg(row + lane + 32 * v, T.a[i][v]);
-                                    if (UPPER) out[lane + 32 * v] = T.a[i][v];
-                                }
-                        }
-                    }
+                    store_tile(perm);
                 } else if (type == REC_BEGIN_ZERO) {
                     row0 = (int) h.y;
                     w = (int) h.z;
@@ -430,6 +485,10 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
             }
         }
         __syncwarp();
+        if (a.trace && lane == 0) {
+            a.trace[8 * (size_t) task + 2] = global_ns();
+            a.trace[8 * (size_t) task + 3] = (unsigned long long) wait_cycles;
+        }
         if (lane == 0) st_release_gpu(a.done + task, epoch);
     }
 }

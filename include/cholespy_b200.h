@@ -87,6 +87,11 @@ int chb_solver_info(const chb_solver *s, int64_t *out, int cap);
  * level_of_row[n] (the reference's level_ind) and order[n] (the reference's levels array). */
 int chb_solver_get_analysis(const chb_solver *s, int lower, int32_t *level_of_row, int32_t *order);
 int chb_solver_get_perm(const chb_solver *s, int32_t *perm);
+/* Debug timeline of the last solve's tasks (only when the solver was created with CHB_TRACE=1 in the
+ * environment): 8 words per task {start ns, slab resident ns, end ns, cycles spent waiting on flags,
+ * last wait returned ns, blocks done ns, triangle done ns, unused}.
+ * Returns the number of words copied. */
+int64_t chb_solver_get_trace(chb_solver *s, int upper, uint64_t *out, int64_t cap);
 
 /* Host factorisation only (CHOLMOD, same options as src/cholesky_solver.cpp:204-238), for factor
  * caching and for handing the same factor to several GPUs. */

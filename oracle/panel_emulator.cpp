@@ -25,7 +25,7 @@ inline float fnma(float a, float b, float c) { return __builtin_fmaf(-a, b, c); 
 inline double fnma(double a, double b, double c) { return __builtin_fma(-a, b, c); }
 inline int span16(uint32_t m) { return m ? 32 - __builtin_clz(m) : 0; }
 
-enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT };
+enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT, END_DENSE };
 
 // returns 0, or a negative error code
 template <typename F>
@@ -124,6 +124,25 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                             const F l = v[idx++];
                             for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(l, acc[(size_t) s * k + c], acc[(size_t) t * k + c]);
                         }
+                    }
+                    for (int i = 0; i < w; ++i)
+                        for (int c = 0; c < k; ++c) {
+                            tmp[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
+                            if (upper) x[(size_t) perm[i] * k + c] = acc[(size_t) i * k + c];
+                        }
+                } break;
+                case END_DENSE: {
+                    if ((int) h[1] != row0 || (int) h[2] != w) return -5;
+                    const int32_t *perm = (const int32_t *) pay;
+                    if (upper) v = (const F *) (pay + 4 * W);
+                    const int wp = w == 1 ? 1 : (w + 3) & ~3;
+                    for (int step = 0; step < wp; ++step) {
+                        const int s = upper ? wp - 1 - step : step;
+                        const F *m = v + (size_t) s * wp;
+                        for (int c = 0; c < k; ++c) acc[(size_t) s * k + c] = acc[(size_t) s * k + c] * m[s];
+                        const int t0 = upper ? 0 : s + 1, t1 = upper ? s : wp;
+                        for (int t = t0; t < t1; ++t)
+                            for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(m[t], acc[(size_t) s * k + c], acc[(size_t) t * k + c]);
                     }
                     for (int i = 0; i < w; ++i)
                         for (int c = 0; c < k; ++c) {
