@@ -328,7 +328,7 @@ CHB_API int chb_schedule_sweep(const chb_schedule *s, int upper, const void **sl
     *tasks = img.tasks.data();
     *order = img.order.data();
     const int64_t v[] = {(int64_t) img.tasks.size(), (int64_t) img.slab.size(), img.page_bytes, img.n_slots, img.n_levels,
-                         img.n_values, img.n_stored_values, img.n_blocks, s->structure.n_panels, s->structure.n_supernodes};
+                         img.n_values, img.n_stored_values, img.n_blocks, s->structure.n_panels, img.max_local_rows};
     int m = (int) (sizeof(v) / sizeof(v[0]));
     if (cap < m) m = cap;
     std::memcpy(info, v, sizeof(int64_t) * (size_t) m);

@@ -16,8 +16,9 @@ namespace chb {
 namespace {
 
 constexpr int kAnalysisBlock = 256;  // threads per CTA of the analysis kernel
-constexpr int kSweepBlock = 128;     // threads per CTA of the sweeps (4 independent warps; sweep.cuh)
-constexpr int kSweepStages = 3;      // pages in flight per warp (sweep.cuh: kStages)
+constexpr int kSweepStages = 4;      // pages in the CTA's slab ring (sweep.cuh: kStages)
+constexpr int kSweepRowBars = 16;    // sweep.cuh: kRowBars
+constexpr int kSweepTaskQueue = 4;   // sweep.cuh: kTaskQueue
 constexpr int kFuncAttrMaxDynamicSharedSize = 8;  // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES
 
 void *dev_alloc(size_t bytes) {
@@ -74,12 +75,19 @@ void csc_to_csr_pattern(int n, const std::vector<int> &colptr, const std::vector
 
 int padded_rhs(int k) { return (k + 3) & ~3; }  // row stride of the work vector (whole 16-byte chunks)
 
-// Dynamic shared memory of one sweep CTA (sweep.cuh): slab rings + row rings + mbarriers.
-size_t sweep_smem_bytes(int elem, int k) {
-    const size_t warps = kSweepBlock / 32;
-    const size_t row_slots = 16;  // sweep.cuh: row_slots()
-    return warps * kSweepStages * (size_t) page_bytes_for(elem) + warps * row_slots * (size_t) padded_rhs(k) * (size_t) elem +
-           warps * kSweepStages * 8;
+int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 RHS columns (+ 1 loader warp)
+
+// Rows of the shared-memory row ring: about 32 KB worth, at least two full blocks.
+int sweep_ring_rows(int elem, int k) {
+    const int row_bytes = padded_rhs(k) * elem;
+    return std::max(32, std::min(128, (32 << 10) / row_bytes));
+}
+
+// Dynamic shared memory of one sweep CTA (sweep.cuh: struct Smem).
+size_t sweep_smem_bytes(int elem, int k, int local_rows) {
+    const size_t row_bytes = (size_t) padded_rhs(k) * (size_t) elem;
+    return kSweepStages * (size_t) page_bytes_for(elem) + ((size_t) sweep_ring_rows(elem, k) + (size_t) local_rows) * row_bytes +
+           (2 * kSweepStages + 2 * kSweepRowBars + 2 * kSweepTaskQueue) * 8 + kSweepTaskQueue * 32 + kSweepRowBars * 4;
 }
 
 }  // namespace
@@ -89,6 +97,7 @@ void ImageShape::to_words(int64_t *w) const {
     for (int u = 0; u < 2; ++u) {
         w[2 + u] = n_tasks[u], w[4 + u] = (int64_t) slab_bytes[u], w[6 + u] = n_slots[u], w[8 + u] = n_task_levels[u];
         w[10 + u] = n_levels[u];
+        w[12 + u] = max_local_rows[u];
     }
 }
 ImageShape ImageShape::from_words(const int64_t *w) {
@@ -97,6 +106,7 @@ ImageShape ImageShape::from_words(const int64_t *w) {
     for (int u = 0; u < 2; ++u) {
         s.n_tasks[u] = w[2 + u], s.slab_bytes[u] = w[4 + u], s.n_slots[u] = w[6 + u], s.n_task_levels[u] = w[8 + u];
         s.n_levels[u] = w[10 + u];
+        s.max_local_rows[u] = w[12 + u];
     }
     return s;
 }
@@ -104,7 +114,6 @@ ImageShape ImageShape::from_words(const int64_t *w) {
 void GpuSolver::allocate_sweep(SweepDev &s) {
     s.slab = dev_alloc(s.slab_bytes);
     s.tasks = dev_alloc(sizeof(SweepTask) * (size_t) s.n_tasks);
-    s.order = dev_alloc(sizeof(int) * (size_t) s.n_tasks);
     s.done = dev_alloc(sizeof(int) * (size_t) s.n_tasks);
     cuda_check(cuMemsetD32Async(s.done, 0, (size_t) std::max(s.n_tasks, 1), nullptr));
     const char *trace = std::getenv("CHB_TRACE");
@@ -130,11 +139,17 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
     d.slab_bytes = img.slab.size();
     d.n_slots = img.n_slots;
     d.n_task_levels = img.n_levels;
+    d.max_local_rows = img.max_local_rows;
     d.n_stored_values = img.n_stored_values;
     allocate_sweep(d);
+    // device task table in ticket order; the `level` word carries the task id (its flag index)
+    std::vector<TaskDesc> by_ticket(img.tasks.size());
+    for (size_t t = 0; t < img.order.size(); ++t) {
+        by_ticket[t] = img.tasks[(size_t) img.order[t]];
+        by_ticket[t].level = (uint32_t) img.order[t];
+    }
     h2d(d.slab, img.slab.data(), img.slab.size());
-    h2d(d.tasks, img.tasks.data(), sizeof(TaskDesc) * img.tasks.size());
-    h2d(d.order, img.order.data(), sizeof(int32_t) * img.order.size());
+    h2d(d.tasks, by_ticket.data(), sizeof(TaskDesc) * by_ticket.size());
     sync0();
 }
 
@@ -231,6 +246,7 @@ GpuSolver::GpuSolver(int device, int elem_size, const ImageShape &shape)
         m_sweep[u].slab_bytes = (uint64_t) shape.slab_bytes[u];
         m_sweep[u].n_slots = (int) shape.n_slots[u];
         m_sweep[u].n_task_levels = (int) shape.n_task_levels[u];
+        m_sweep[u].max_local_rows = (int) shape.max_local_rows[u];
         allocate_sweep(m_sweep[u]);
     }
     m_lower.n_levels = (int) shape.n_levels[0];
@@ -245,7 +261,6 @@ GpuSolver::~GpuSolver() {
     for (SweepDev &s : m_sweep) {
         dev_free(s.slab);
         dev_free(s.tasks);
-        dev_free(s.order);
         dev_free(s.done);
         dev_free(s.trace);
     }
@@ -264,6 +279,7 @@ ImageShape GpuSolver::shape() const {
         s.slab_bytes[u] = (int64_t) m_sweep[u].slab_bytes;
         s.n_slots[u] = m_sweep[u].n_slots;
         s.n_task_levels[u] = m_sweep[u].n_task_levels;
+        s.max_local_rows[u] = m_sweep[u].max_local_rows;
     }
     s.n_levels[0] = m_lower.n_levels;
     s.n_levels[1] = m_upper.n_levels;
@@ -272,22 +288,23 @@ ImageShape GpuSolver::shape() const {
 
 std::vector<ImageBuffer> GpuSolver::image() const {
     std::vector<ImageBuffer> out;
-    static const char *names[2][3] = {{"lower.slab", "lower.tasks", "lower.order"}, {"upper.slab", "upper.tasks", "upper.order"}};
+    static const char *names[2][2] = {{"lower.slab", "lower.tasks"}, {"upper.slab", "upper.tasks"}};
     for (int u = 0; u < 2; ++u) {
         const SweepDev &s = m_sweep[u];
         out.push_back({names[u][0], s.slab, (size_t) s.slab_bytes});
         out.push_back({names[u][1], s.tasks, sizeof(SweepTask) * (size_t) s.n_tasks});
-        out.push_back({names[u][2], s.order, sizeof(int) * (size_t) s.n_tasks});
     }
     return out;
 }
 
 void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
     char name[64];
-    snprintf(name, sizeof name, "chb_sweep_%s_%d_%s", m_elem == 4 ? "f32" : "f64", (k + 31) / 32, upper ? "upper" : "lower");
+    snprintf(name, sizeof name, "chb_sweep_%s_%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower");
     CUfunction fn = kernel(m_dev, name);
     if (!fn) throw std::runtime_error(driver_error_text());
-    const size_t smem = sweep_smem_bytes(m_elem, k);
+    const int local_rows = std::max(m_sweep[0].max_local_rows, m_sweep[1].max_local_rows);
+    const size_t smem = sweep_smem_bytes(m_elem, k, local_rows);
+    const int block = 32 * (sweep_warps(k) + 1);
     cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
 
     int *counters = (int *) m_counters;
@@ -301,10 +318,11 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
         a.n_tasks = s.n_tasks;
         a.k = k;
         a.epoch = m_epoch;
+        a.local_rows = local_rows;
+        a.ring_rows = sweep_ring_rows(m_elem, k);
         a.reserved = 0;
         a.slab = (const unsigned char *) s.slab;
         a.tasks = (const SweepTask *) s.tasks;
-        a.order = (const int *) s.order;
         a.done = (int *) s.done;
         a.ticket = ticket;
         a.ticket_next = ticket_next;
@@ -324,12 +342,10 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
         fill(a64);
         params[0] = &a64;
     }
-    const int warps_per_block = kSweepBlock / 32;
-    const int needed = (s.n_tasks + warps_per_block - 1) / warps_per_block;
-    int grid = std::max(1, std::min(needed, max_resident_blocks(m_dev, fn, kSweepBlock, smem)));
+    int grid = std::max(1, std::min(s.n_tasks, max_resident_blocks(m_dev, fn, block, smem)));
     if (const char *cap = std::getenv("CHB_SWEEP_CTAS_PER_SM")) grid = std::max(1, std::min(grid, std::atoi(cap) * m_dev->sm_count));
     m_last_grid = grid;
-    cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, kSweepBlock, 1, 1, (unsigned) smem, nullptr, params));
+    cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, block, 1, 1, (unsigned) smem, nullptr, params));
 }
 
 void GpuSolver::solve(int k, const void *b, void *x) {
@@ -343,7 +359,7 @@ void GpuSolver::solve(int k, const void *b, void *x) {
         dev_free(m_scratch);
         m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) padded_rhs(k));
         const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
-        m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) k);
+        m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) padded_rhs(k));
         m_k = k;
     }
     m_epoch += 1;

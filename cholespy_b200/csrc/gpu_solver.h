@@ -24,14 +24,14 @@ struct TriangleAnalysis {
 // One sweep's image in HBM (see panel_schedule.h).
 struct SweepDev {
     void *slab = nullptr;    // record stream
-    void *tasks = nullptr;   // SweepTask[n_tasks]
-    void *order = nullptr;   // int32[n_tasks]: ticket -> task
+    void *tasks = nullptr;   // SweepTask[n_tasks], in ticket order
     void *done = nullptr;    // int32[n_tasks]: epoch flags (scratch, not part of the image)
     void *trace = nullptr;   // uint64[8 * n_tasks] when CHB_TRACE=1 (debug timeline), else null
     int n_tasks = 0;
     uint64_t slab_bytes = 0;
     int n_slots = 0;
     int n_task_levels = 0;
+    int max_local_rows = 0;  // largest local task (rows held in shared memory)
     int64_t n_stored_values = 0;
 };
 
@@ -46,7 +46,8 @@ struct ImageShape {
     int64_t n = 0, nnz = 0;
     int64_t n_tasks[2] = {0, 0}, slab_bytes[2] = {0, 0}, n_slots[2] = {0, 0}, n_task_levels[2] = {0, 0};
     int64_t n_levels[2] = {0, 0};  // reference level counts (lower, upper)
-    static constexpr int kWords = 12;
+    int64_t max_local_rows[2] = {0, 0};
+    static constexpr int kWords = 14;
     void to_words(int64_t *w) const;
     static ImageShape from_words(const int64_t *w);
 };

@@ -16,10 +16,11 @@ struct AnalysisArgs {
 };
 
 // One panel sweep (kernels.cu: chb_sweep_*).  See panel_schedule.h for the slab/record format.
+// Device task table, in TICKET order (dependencies first): entry t is what the worker drawing ticket t runs.
 struct SweepTask {
     unsigned long long offset;  // byte offset of the task's slab
     unsigned int bytes;
-    unsigned int level;
+    unsigned int level;         // on the device: the task's id (index of its ready flag; wait codes are id + 1)
 };
 
 template <typename Float>
@@ -27,17 +28,18 @@ struct SweepArgs {
     int n_tasks;
     int k;
     int epoch;
+    int local_rows;       // largest local task (rows of the shared-memory local area)
+    int ring_rows;        // rows of the shared-memory row ring
     int reserved;
     const unsigned char *slab;
-    const SweepTask *tasks;
-    const int *order;     // ticket -> task id (dependencies first)
+    const SweepTask *tasks;     // ticket-ordered
     int *done;            // per-task epoch flags
     int *ticket;          // this sweep's ticket counter
     int *ticket_next;     // the other sweep's counter: cleared here
     Float *tmp;           // (n, k) work vector in permuted order
     const Float *src;     // forward: user's b
     Float *dst;           // backward: user's x
-    Float *scratch;       // n_slots tiles of 16 x k
+    Float *scratch;       // n_slots tiles of 16 x round4(k)
     unsigned long long *trace;  // optional (debug): 8 words per task {start ns, slab ready ns, end ns, cycles spent waiting, last wait ns, blocks done ns, triangle done ns, -}
 };
 

@@ -41,6 +41,7 @@ public:
         }
     }
     void put_int(size_t payload_off, size_t index, int32_t v) { std::memcpy(&m_buf[payload_off + 4 * index], &v, 4); }
+    void put_bytes(size_t payload_off, const void *src, size_t n) { std::memcpy(&m_buf[payload_off], src, n); }
 
 private:
     void header(uint32_t type, int32_t a, uint32_t b, uint32_t c, size_t len) {
@@ -64,8 +65,9 @@ ScheduleOptions schedule_options_from_env() {
         return v && *v ? std::atoi(v) : dflt;
     };
     o.exact_order = geti("CHB_EXACT_ORDER", 0) != 0;
-    o.group_cost = std::max(1, geti("CHB_GROUP_COST", o.group_cost));
-    o.group_panels = std::max(1, geti("CHB_GROUP_PANELS", o.group_panels));
+    o.local_rows = std::max(0, std::min(240, geti("CHB_LOCAL_ROWS", o.local_rows)));
+    o.local_ext = std::max(0, geti("CHB_LOCAL_EXT", o.local_ext));
+    o.local_cost = std::max(1, geti("CHB_LOCAL_COST", o.local_cost));
     o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));
     o.chunk_cost = std::max(256, geti("CHB_CHUNK_COST", o.chunk_cost));
     if (const char *v = std::getenv("CHB_RELAX_ALPHA")) o.relax_alpha = std::max(1.0, std::atof(v));
@@ -179,6 +181,10 @@ struct Builder {
     std::vector<int> task_of_panel;
     int cur = -1;
     uint32_t cur_level = 0;
+    // local task being emitted (see REC_LOCAL_LOAD): unknowns [loc_lo, loc_lo + loc_n_int), then the external rows
+    bool local = false;
+    int loc_lo = 0, loc_n_int = 0;
+    std::vector<int> loc_ext;
 
     Builder(const HostFactor &L_, const PanelStructure &S_, const ScheduleOptions &o, SweepImage &i)
         : L(L_), S(S_), opt(o), img(i), w(i.slab, i.page_bytes, i.elem), upper(i.upper), task_of_panel(S_.n_panels, -1) {}
@@ -269,9 +275,19 @@ struct Builder {
     }
 
     // -- records --------------------------------------------------------------------------------
+    uint32_t flag() const { return local ? (uint32_t) REC_LOCAL_FLAG : 0u; }
+    int local_index(int row) const {
+        if (row >= loc_lo && row < loc_lo + loc_n_int) return row - loc_lo;
+        const auto it = std::lower_bound(loc_ext.begin(), loc_ext.end(), row);
+        if (it == loc_ext.end() || *it != row) throw std::logic_error("panel schedule: local task reads a row it did not load");
+        return loc_n_int + (int) (it - loc_ext.begin());
+    }
+
     void emit_begin_rhs(int P) {
         const int wd = S.width(P), row0 = S.c0[P];
-        if (upper) {
+        if (local) {
+            w.record(REC_BEGIN_RHS | REC_LOCAL_FLAG, row0 - loc_lo, (uint32_t) wd, 0, 0);
+        } else if (upper) {
             w.record(REC_BEGIN_RHS, row0, (uint32_t) wd, 0, 0);
         } else {
             const size_t off = w.record(REC_BEGIN_RHS, row0, (uint32_t) wd, 0, 4 * kPanelWidth);
@@ -293,16 +309,30 @@ struct Builder {
         img.n_blocks += 1;
         double buf[kPanelWidth][kPanelWidth];  // [row of the block][column of p]
         img.n_values += gather_block(p, q0, nr, buf);
+        // local tasks: 16 bytes of local source-row indices (sweep order) precede the values
+        const size_t idx_bytes = local ? 16 : 0;
+        auto put_sources = [&](size_t off, int first_row, uint32_t mask, bool descending) {
+            if (!local) return;
+            uint8_t idx[16] = {0};
+            int r = 0;
+            for (int bit = 0; bit < kPanelWidth; ++bit) {
+                const int sbit = descending ? kPanelWidth - 1 - bit : bit;
+                if (mask >> sbit & 1) idx[r++] = (uint8_t) local_index(first_row + sbit);
+            }
+            w.put_bytes(off, idx, 16);
+        };
         if (upper) {
             // unknowns = columns of p (all wd of them); sources = rows of t present in the block,
             // visited in DESCENDING row order (reference walks a row of L' from its end backwards)
             const int wd = S.width(p);
             const uint32_t tmask = (1u << wd) - 1;
-            const uint32_t wait = wait_code(task_of_panel[t]);
+            const uint32_t wait = local ? 0u : wait_code(task_of_panel[t]);
             const bool thin = wd <= 3;
             const int stride = thin ? wd : (wd + 3) & ~3;
-            const size_t off = w.record(thin ? REC_BLOCK_D1 : REC_BLOCK_D4, S.c0[t], rows | tmask << 16, wait,
-                                        es * (size_t) nr * (size_t) stride);
+            const size_t off0 = w.record((thin ? REC_BLOCK_D1 : REC_BLOCK_D4) | flag(), S.c0[t], rows | tmask << 16, wait,
+                                         idx_bytes + es * (size_t) nr * (size_t) stride);
+            put_sources(off0, S.c0[t], rows, true);
+            const size_t off = off0 + idx_bytes;
             for (int s = 0; s < nr; ++s)
                 for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) s * stride + j, buf[nr - 1 - s][j]);
             img.n_stored_values += (int64_t) nr * stride;
@@ -311,10 +341,13 @@ struct Builder {
             (void) P;
             const int wd = S.width(p);
             const uint32_t smask = (1u << wd) - 1;
-            const uint32_t wait = wait_code(task_of_panel[p]);
+            const uint32_t wait = local ? 0u : wait_code(task_of_panel[p]);
             const int stride = (span16(rows) + 3) & ~3;
             if (2 * nr >= stride) {
-                const size_t off = w.record(REC_BLOCK_D4, S.c0[p], smask | rows << 16, wait, es * (size_t) wd * (size_t) stride);
+                const size_t off0 = w.record(REC_BLOCK_D4 | flag(), S.c0[p], smask | rows << 16, wait,
+                                             idx_bytes + es * (size_t) wd * (size_t) stride);
+                put_sources(off0, S.c0[p], smask, false);
+                const size_t off = off0 + idx_bytes;
                 for (int j = 0; j < wd; ++j) {
                     int q = 0;
                     for (int tt = 0; tt < stride; ++tt)
@@ -322,7 +355,10 @@ struct Builder {
                 }
                 img.n_stored_values += (int64_t) wd * stride;
             } else {
-                const size_t off = w.record(REC_BLOCK_TM, S.c0[p], smask | rows << 16, wait, es * (size_t) nr * (size_t) wd);
+                const size_t off0 = w.record(REC_BLOCK_TM | flag(), S.c0[p], smask | rows << 16, wait,
+                                             idx_bytes + es * (size_t) nr * (size_t) wd);
+                put_sources(off0, S.c0[p], smask, false);
+                const size_t off = off0 + idx_bytes;
                 for (int r = 0; r < nr; ++r)
                     for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) r * wd + j, buf[r][j]);
                 img.n_stored_values += (int64_t) nr * wd;
@@ -338,9 +374,10 @@ struct Builder {
         const int wd = S.width(P), row0 = S.c0[P];
         const size_t es = (size_t) img.elem;
         const int wp = wd == 1 ? 1 : (wd + 3) & ~3;
-        const size_t head = upper ? 4 * kPanelWidth : 0;
-        const size_t off = w.record(REC_END_DENSE, row0, (uint32_t) wd, 0, head + es * (size_t) (wp * wp));
-        if (upper)
+        const size_t head = upper && !local ? 4 * kPanelWidth : 0;
+        const size_t off = w.record(REC_END_DENSE | flag(), local ? row0 - loc_lo : row0, (uint32_t) wd, 0,
+                                    head + es * (size_t) (wp * wp));
+        if (head)
             for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
         int present = 0;
         for (int s = 0; s < wp; ++s) {
@@ -361,9 +398,9 @@ struct Builder {
         const int wd = S.width(P), row0 = S.c0[P];
         const size_t es = (size_t) img.elem;
         const size_t tri_bytes = round16(es * (size_t) (wd * (wd + 1) / 2));
-        const size_t head = upper ? 4 * kPanelWidth : 0;  // backward: perm[16] first (x is scattered through it)
-        const size_t off = w.record(REC_END_FINAL, row0, (uint32_t) wd, 0, head + tri_bytes);
-        if (upper)
+        const size_t head = upper && !local ? 4 * kPanelWidth : 0;  // backward: perm[16] first (x is scattered through it)
+        const size_t off = w.record(REC_END_FINAL | flag(), local ? row0 - loc_lo : row0, (uint32_t) wd, 0, head + tri_bytes);
+        if (head)
             for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
         size_t idx = 0;
         int present = 0;
@@ -431,12 +468,58 @@ struct Builder {
         close_task();
     }
 
+    // One LOCAL task: the complete subtree of panels [lo, hi] (hi = its root), solved in shared memory.
+    void emit_local_task(int lo, int hi, std::vector<int64_t> &blocks) {
+        open_task();
+        local = true;
+        loc_lo = S.c0[lo];
+        loc_n_int = S.c0[hi + 1] - loc_lo;
+        loc_ext.clear();
+        std::vector<uint32_t> waits;
+        if (upper) {
+            // every row the subtree reads from outside lies in the below-panel row list of its root
+            loc_ext.assign(S.rows.begin() + S.rlo[hi], S.rows.begin() + S.rlo[hi] + S.m[hi]);
+            for (int r : loc_ext) {
+                const uint32_t code = wait_code(task_of_panel[S.panel_of_row[r]]);
+                if (code && std::find(waits.begin(), waits.end(), code) == waits.end()) waits.push_back(code);
+            }
+        }
+        const int n_ext = (int) loc_ext.size(), n_wait = (int) waits.size();
+        img.max_local_rows = std::max(img.max_local_rows, loc_n_int + n_ext);
+        auto pad4 = [](int v) { return (size_t) ((v + 3) & ~3); };
+        {
+            const size_t bytes = upper ? 4 * (pad4(n_ext) + pad4(n_wait)) : 4 * pad4(loc_n_int);
+            const size_t off = w.record(REC_LOCAL_LOAD, loc_lo, (uint32_t) loc_n_int | (uint32_t) n_ext << 16, (uint32_t) n_wait, bytes);
+            if (upper) {
+                for (int e = 0; e < n_ext; ++e) w.put_int(off, (size_t) e, loc_ext[e]);
+                for (int e = 0; e < n_wait; ++e) w.put_int(off, pad4(n_ext) + (size_t) e, (int32_t) waits[e]);
+            } else {
+                for (int i = 0; i < loc_n_int; ++i) w.put_int(off, (size_t) i, L.perm[loc_lo + i]);
+            }
+        }
+        for (int c = 0; c <= hi - lo; ++c) {
+            const int P = upper ? hi - c : lo + c;
+            blocks_of(P, blocks);
+            emit_begin_rhs(P);
+            for (int64_t b : blocks) emit_block(P, b);
+            emit_end_final(P);
+        }
+        {
+            const size_t off = w.record(REC_LOCAL_STORE, loc_lo, (uint32_t) loc_n_int, 0, upper ? 4 * pad4(loc_n_int) : 0);
+            if (upper)
+                for (int i = 0; i < loc_n_int; ++i) w.put_int(off, (size_t) i, L.perm[loc_lo + i]);
+        }
+        local = false;
+        close_task();
+    }
+
     void run() {
         const int np = S.n_panels;
         std::vector<int64_t> blocks;
-        // Tasks of several panels are COMPLETE SUBTREES of the panel elimination tree (a contiguous
-        // index range, the factor being postordered): everything outside such a task depends on it
-        // only through its root, so fusing it adds no false dependency in either sweep.
+        // LOCAL tasks are COMPLETE SUBTREES of the panel elimination tree (a contiguous index range,
+        // the factor being postordered): everything outside such a task depends on it only through
+        // its root, so fusing it adds no false dependency in either sweep, and everything it reads
+        // from outside lies in the root's below-panel row list.
         std::vector<int64_t> sub_cost(np);
         std::vector<int> sub_count(np, 1), first(np);
         for (int P = 0; P < np; ++P) {
@@ -454,13 +537,14 @@ struct Builder {
             sub_count[q] += sub_count[P];
             first[q] = std::min(first[q], first[P]);
         }
-        std::vector<int> root_of(np);
-        for (int P = 0; P < np; ++P) root_of[P] = P;
+        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 32 : 64);
+        std::vector<int> root_of(np, -1);  // root of the local task a panel belongs to, or -1
         for (int P = np - 1; P >= 0; --P) {
-            if (root_of[P] != P) continue;  // already inside a fused subtree
+            if (root_of[P] >= 0) continue;  // already inside a local subtree
             const bool contiguous = sub_count[P] == P - first[P] + 1;
-            if (sub_count[P] > 1 && contiguous && sub_cost[P] <= opt.group_cost && sub_count[P] <= opt.group_panels)
-                for (int q = first[P]; q < P; ++q) root_of[q] = P;
+            const int rows = S.c0[P + 1] - S.c0[first[P]];
+            if (contiguous && rows <= max_rows && S.m[P] <= opt.local_ext && rows + S.m[P] <= 255 && sub_cost[P] <= opt.local_cost)
+                for (int q = first[P]; q <= P; ++q) root_of[q] = P;
         }
         int i = 0;
         while (i < np) {
@@ -468,23 +552,24 @@ struct Builder {
             int lo, hi;
             if (!upper) {
                 lo = i;
-                hi = root_of[i];
+                hi = root_of[i] >= 0 ? root_of[i] : i;
             } else {
                 hi = np - 1 - i;
-                lo = root_of[hi] == hi && sub_count[hi] == hi - first[hi] + 1 && first[hi] < hi && root_of[first[hi]] == hi ? first[hi] : hi;
+                lo = root_of[hi] >= 0 ? first[hi] : hi;
+                if (root_of[hi] >= 0 && root_of[hi] != hi) throw std::logic_error("panel schedule: local subtree is not contiguous");
             }
             i += hi - lo + 1;
-            if (lo == hi && cost[lo] > opt.split_cost) {
-                blocks_of(lo, blocks);
+            if (root_of[hi] >= 0) {
+                emit_local_task(lo, hi, blocks);
+                continue;
+            }
+            blocks_of(lo, blocks);
+            if (cost[lo] > opt.split_cost) {
                 emit_split_panel(lo, blocks);
                 continue;
             }
             open_task();
-            for (int c = 0; c <= hi - lo; ++c) {
-                const int P = upper ? hi - c : lo + c;
-                blocks_of(P, blocks);
-                emit_panel(P, blocks);
-            }
+            emit_panel(lo, blocks);
             close_task();
         }
     }

@@ -15,8 +15,16 @@
 //           amalgamated ("relaxed"), their absent entries stored as explicit zeros.
 //   block   the dense rectangle L[R ∩ rows(panel t), cols(panel p)]: "block (t, p)".
 //   tile    the w x n_rhs slab of unknowns of one panel, held in registers by one warp.
-//   task    what one warp executes for one ticket: a run of consecutive small panels, or one panel,
-//           or one chunk of the blocks of a large panel (partial sums parked in a scratch slot).
+//   task    what one worker (a CTA of 1-4 warps, each owning 32 RHS columns) executes for one ticket:
+//           a LOCAL task (a complete subtree of small panels, solved entirely in shared memory), or
+//           one panel, or one chunk of the blocks of a large panel (partial sums parked in a
+//           scratch slot).
+//   local   a task whose unknowns (<= local_rows rows, one contiguous index range: the factor is
+//           postordered, so a complete subtree is contiguous) are loaded into shared memory once,
+//           together with the <= local_ext already-solved external rows the backward sweep needs
+//           (all inside the subtree root's below-panel row list), solved there record by record
+//           with no global-memory traffic, and written back once.  The forward sweep of a
+//           complete subtree has no external dependency at all.
 //   slab    the byte stream of one task: 16-byte-aligned records (below), streamed through shared
 //           memory in pages by 1-D TMA bulk copies; no record straddles a page boundary.
 //
@@ -55,11 +63,24 @@ enum RecordType : uint32_t {
     REC_END_SLOT = 9,    // b = slot << 8.  park the tile in a scratch slot
     REC_END_DENSE = 10,  // a = row0, b = w.  like END_FINAL with the triangle as a dense wp x wp matrix (wp = 1 or
                          // round4(w)) holding RECIPROCAL pivots: multiply instead of divide (fast mode only)
+    REC_LOCAL_LOAD = 11, // a = row_lo, b = n_int | n_ext << 16, c = n_wait.  payload (int32 each, every list padded
+                         // to 4 entries): forward perm[n_int]; backward ext_row[n_ext], wait_code[n_wait].
+                         // local[0..n_int) = rhs rows (forward: b[perm[i]]; backward: tmp[row_lo + i]),
+                         // local[n_int + e] = tmp[ext_row[e]] after every wait code has published
+    REC_LOCAL_STORE = 12,// a = row_lo, b = n_int.  payload backward: perm[n_int].  tmp[row_lo + i] = local[i]
+                         // (backward: also x[perm[i]] = local[i]); the task's last record
+    // Inside a local task the BEGIN_RHS / BLOCK_* / END_FINAL / END_DENSE records carry REC_LOCAL_FLAG:
+    //   BEGIN_RHS: a = local index of the panel's first row, no payload (tile = local rows)
+    //   BLOCK_*:   a unused, c = 0; payload starts with 16 bytes = local index of each source row in
+    //              sweep order, then the values as usual
+    //   END_*:     a = local index of the panel's first row; no perm payload; the tile goes back to local rows
+    REC_LOCAL_FLAG = 0x40,
 };
 
 struct ScheduleOptions {
-    int group_cost = 2048;    // a whole subtree of panels is fused into one task up to this many values
-    int group_panels = 32;    // ... and at most this many panels
+    int local_rows = 0;       // a complete subtree becomes one LOCAL task up to this many rows (0: 64 f32 / 32 f64)
+    int local_ext = 32;       // ... this many external rows below its root panel (backward sweep)
+    int local_cost = 16384;   // ... and this many stored values
     int split_cost = 8192;    // a panel with more values than this is split into chunk tasks
     int chunk_cost = 4096;    // values per chunk task
     double relax_alpha = 1.5; // relaxed panels: stored values <= alpha * non-zeros + beta (1.0 / 0: no fill)
@@ -100,11 +121,12 @@ struct SweepImage {
     bool upper = false;
     int elem = 4;
     int n = 0;
-    int page_bytes = 2048;
+    int page_bytes = 4096;
     std::vector<uint8_t> slab;
     std::vector<TaskDesc> tasks;
     std::vector<int32_t> order;      // ticket -> task id, sorted by level (dependencies first)
     int n_slots = 0;                 // scratch tiles (kPanelWidth x n_rhs elements each)
+    int max_local_rows = 0;          // largest n_int + n_ext over the local tasks (sizes the kernels' shared memory)
     int n_levels = 0;
     int64_t n_values = 0;            // factor values referenced (== nnz(L))
     int64_t n_stored_values = 0;     // including zero fill
@@ -115,9 +137,9 @@ void build_panel_structure(const HostFactor &L, const ScheduleOptions &opt, Pane
 void build_sweep_image(const HostFactor &L, const PanelStructure &S, int elem_size, bool upper,
                        const ScheduleOptions &opt, SweepImage *out);
 
-inline int page_bytes_for(int elem_size) { return elem_size == 8 ? 4096 : 2048; }
-// Defaults, overridable for tuning / parity runs: CHB_EXACT_ORDER=1, CHB_GROUP_COST, CHB_GROUP_PANELS,
-// CHB_SPLIT_COST, CHB_CHUNK_COST, CHB_RELAX_ALPHA, CHB_RELAX_BETA.
+inline int page_bytes_for(int) { return 4096; }
+// Defaults, overridable for tuning / parity runs: CHB_EXACT_ORDER=1, CHB_LOCAL_ROWS, CHB_LOCAL_EXT,
+// CHB_LOCAL_COST, CHB_SPLIT_COST, CHB_CHUNK_COST, CHB_RELAX_ALPHA, CHB_RELAX_BETA.
 ScheduleOptions schedule_options_from_env();
 
 }  // namespace chb

@@ -106,7 +106,7 @@ void chb_factor_destroy(chb_factor *f);
  * orders): build the solver on one GPU, read its shape, create empty replicas of the same shape on
  * the others, and broadcast each image buffer (NCCL) from the source into the replica.  New; the
  * reference is single-GPU.  shape = CHB_IMAGE_SHAPE_WORDS int64 words. */
-#define CHB_IMAGE_SHAPE_WORDS 12
+#define CHB_IMAGE_SHAPE_WORDS 14
 int chb_solver_image_shape(const chb_solver *s, int64_t *shape, int cap);
 int chb_solver_create_replica(chb_solver **out, int dtype, const int64_t *shape, int n_words, int device);
 int chb_solver_image_count(const chb_solver *s);
@@ -121,7 +121,7 @@ typedef struct chb_schedule chb_schedule;
 int chb_schedule_create(chb_schedule **out, int dtype, int n, int64_t nnz_l, const int32_t *l_colptr,
                         const int32_t *l_rowidx, const double *l_vals, const int32_t *perm, int exact_order);
 /* info[0..9] = n_tasks, slab bytes, page bytes, n_slots, n_levels, n_values, n_stored_values, n_blocks,
- * n_panels, n_supernodes.  tasks = array of {uint64 offset, uint32 bytes, uint32 level}. */
+ * n_panels, max_local_rows (largest row count a local task holds in shared memory).  tasks = array of {uint64 offset, uint32 bytes, uint32 level}. */
 int chb_schedule_sweep(const chb_schedule *s, int upper, const void **slab, const void **tasks, const int32_t **order,
                        int64_t *info, int cap);
 void chb_schedule_destroy(chb_schedule *s);

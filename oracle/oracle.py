@@ -192,7 +192,7 @@ def _load_emu():
 
 
 SCHEDULE_INFO_KEYS = ("n_tasks", "slab_bytes", "page_bytes", "n_slots", "n_levels", "n_values", "n_stored_values",
-                      "n_blocks", "n_panels", "n_supernodes")
+                      "n_blocks", "n_panels", "max_local_rows")
 
 
 def schedule_solve(lib, l_colptr, l_rowidx, l_vals, perm, b, exact_order=-1):

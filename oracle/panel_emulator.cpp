@@ -25,7 +25,8 @@ inline float fnma(float a, float b, float c) { return __builtin_fmaf(-a, b, c); 
 inline double fnma(double a, double b, double c) { return __builtin_fma(-a, b, c); }
 inline int span16(uint32_t m) { return m ? 32 - __builtin_clz(m) : 0; }
 
-enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT, END_DENSE };
+enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT, END_DENSE,
+       LOCAL_LOAD, LOCAL_STORE, LOCAL_FLAG = 0x40 };
 
 // returns 0, or a negative error code
 template <typename F>
@@ -33,6 +34,8 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
         const F *b, F *x, F *scratch) {
     std::vector<uint8_t> done((size_t) n_tasks, 0);
     std::vector<F> acc((size_t) W * k);
+    std::vector<F> loc;  // rows of the local task being executed: [n_int unknowns | n_ext external rows] x k
+    int loc_rows = 0;
     auto waited = [&](uint32_t c) { return c == 0 || done[c - 1]; };
     for (int ticket = 0; ticket < n_tasks; ++ticket) {
         const int task = order[ticket];
@@ -46,15 +49,59 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
             while (p < plen) {
                 uint32_t h[4];
                 std::memcpy(h, base + pg + p, 16);
-                const uint32_t type = h[0] & 0xff, len = (h[0] >> 8) * 16;
+                const uint32_t type = h[0] & 0x3f, len = (h[0] >> 8) * 16;
+                const bool local = (h[0] & LOCAL_FLAG) != 0;
                 if (len < 16 || p + len > plen) return -3;  // record straddles a page
                 const uint8_t *pay = base + pg + p + 16;
+                const uint8_t *src_idx = pay;  // local blocks: 16 local source-row indices first
+                if (local && type >= BLOCK_D4 && type <= BLOCK_TM) pay += 16;
                 const F *v = (const F *) pay;
+                // row `s` (sweep order rank r) of a block's source panel
+                auto source_row = [&](int src0, int s, int r) -> const F * {
+                    if (!local) return tmp + (size_t) (src0 + s) * k;
+                    if ((int) src_idx[r] >= loc_rows) return nullptr;
+                    return loc.data() + (size_t) src_idx[r] * k;
+                };
                 switch (type) {
                 case NOP: break;
+                case LOCAL_LOAD: {
+                    const int lo = (int) h[1], n_int = (int) (h[2] & 0xffff), n_ext = (int) (h[2] >> 16), n_wait = (int) h[3];
+                    const int32_t *list = (const int32_t *) pay;
+                    loc_rows = n_int + n_ext;
+                    loc.assign((size_t) loc_rows * k, F(0));
+                    if (!upper) {
+                        if (n_ext || n_wait) return -7;
+                        for (int i = 0; i < n_int; ++i)
+                            for (int c = 0; c < k; ++c) loc[(size_t) i * k + c] = b[(size_t) list[i] * k + c];
+                    } else {
+                        const int32_t *waits = list + ((n_ext + 3) & ~3);
+                        for (int e = 0; e < n_wait; ++e)
+                            if (!waited((uint32_t) waits[e])) return -4;
+                        for (int i = 0; i < n_int; ++i)
+                            for (int c = 0; c < k; ++c) loc[(size_t) i * k + c] = tmp[(size_t) (lo + i) * k + c];
+                        for (int e = 0; e < n_ext; ++e)
+                            for (int c = 0; c < k; ++c) loc[(size_t) (n_int + e) * k + c] = tmp[(size_t) list[e] * k + c];
+                    }
+                } break;
+                case LOCAL_STORE: {
+                    const int lo = (int) h[1], n_int = (int) h[2];
+                    const int32_t *perm = (const int32_t *) pay;
+                    for (int i = 0; i < n_int; ++i)
+                        for (int c = 0; c < k; ++c) {
+                            tmp[(size_t) (lo + i) * k + c] = loc[(size_t) i * k + c];
+                            if (upper) x[(size_t) perm[i] * k + c] = loc[(size_t) i * k + c];
+                        }
+                    loc_rows = 0;
+                } break;
                 case BEGIN_RHS: {
                     row0 = (int) h[1], w = (int) h[2];
                     std::fill(acc.begin(), acc.end(), F(0));
+                    if (local) {
+                        if (row0 + w > loc_rows) return -7;
+                        for (int i = 0; i < w; ++i)
+                            for (int c = 0; c < k; ++c) acc[(size_t) i * k + c] = loc[(size_t) (row0 + i) * k + c];
+                        break;
+                    }
                     const int32_t *perm = (const int32_t *) pay;
                     for (int i = 0; i < w; ++i)
                         for (int c = 0; c < k; ++c)
@@ -85,7 +132,8 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                     for (int bit = 0; bit < W; ++bit) {
                         const int s = upper ? W - 1 - bit : bit;
                         if (!(smask >> s & 1)) continue;
-                        const F *srow = tmp + (size_t) (src0 + s) * k;
+                        const F *srow = source_row(src0, s, r);
+                        if (!srow) return -7;
                         for (int t = 0; t < stride; ++t)
                             for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(v[(size_t) r * stride + t], srow[c], acc[(size_t) t * k + c]);
                         ++r;
@@ -103,7 +151,8 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                         for (int bit = 0; bit < W; ++bit) {
                             const int s = upper ? W - 1 - bit : bit;
                             if (!(smask >> s & 1)) continue;
-                            const F *srow = tmp + (size_t) (src0 + s) * k;
+                            const F *srow = source_row(src0, s, sr);
+                            if (!srow) return -7;
                             for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(v[(size_t) r * ns + sr], srow[c], acc[(size_t) t * k + c]);
                             ++sr;
                         }
@@ -113,7 +162,7 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                 case END_FINAL: {
                     if ((int) h[1] != row0 || (int) h[2] != w) return -5;
                     const int32_t *perm = (const int32_t *) pay;
-                    if (upper) v = (const F *) (pay + 4 * W);
+                    if (upper && !local) v = (const F *) (pay + 4 * W);
                     size_t idx = 0;
                     for (int step = 0; step < w; ++step) {
                         const int s = upper ? w - 1 - step : step;
@@ -127,6 +176,10 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                     }
                     for (int i = 0; i < w; ++i)
                         for (int c = 0; c < k; ++c) {
+                            if (local) {
+                                loc[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
+                                continue;
+                            }
                             tmp[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
                             if (upper) x[(size_t) perm[i] * k + c] = acc[(size_t) i * k + c];
                         }
@@ -134,7 +187,7 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                 case END_DENSE: {
                     if ((int) h[1] != row0 || (int) h[2] != w) return -5;
                     const int32_t *perm = (const int32_t *) pay;
-                    if (upper) v = (const F *) (pay + 4 * W);
+                    if (upper && !local) v = (const F *) (pay + 4 * W);
                     const int wp = w == 1 ? 1 : (w + 3) & ~3;
                     for (int step = 0; step < wp; ++step) {
                         const int s = upper ? wp - 1 - step : step;
@@ -146,6 +199,10 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                     }
                     for (int i = 0; i < w; ++i)
                         for (int c = 0; c < k; ++c) {
+                            if (local) {
+                                loc[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
+                                continue;
+                            }
                             tmp[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
                             if (upper) x[(size_t) perm[i] * k + c] = acc[(size_t) i * k + c];
                         }

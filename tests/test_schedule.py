@@ -1,0 +1,37 @@
+"""CPU tests of the sweep schedule the sm_100a kernels stream (csrc/panel_schedule.cpp): the image is
+built through the C ABI (chb_schedule_create, no GPU) and executed by the sequential interpreter
+oracle/panel_emulator.cpp, then compared with the row-by-row oracle (cholespy_oracle.c, which follows
+reference kernels/kernels.cu:81-120,149-190)."""
+import numpy as np
+import pytest
+
+import problems
+from helpers import TOL, factorize, max_rel_err
+
+CASES = ["cube", "ico3", "ico5", "grid2d-40", "grid3d-10", "localspd-30"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", CASES)
+def test_exact_order_schedule_is_bit_identical_to_the_oracle(name, dtype, oracle_mod, native_lib):
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    rng = np.random.default_rng(3)
+    for k in (1, 5, 33):
+        b = rng.random((p["n"], k)).astype(dtype)
+        x_ref = oracle_mod.solve(cp, ri, v, perm, b).astype(dtype)
+        x, fwd, bwd = oracle_mod.schedule_solve(native_lib, cp, ri, v, perm, b, exact_order=1)
+        assert fwd["n_values"] == len(ri) and bwd["n_values"] == len(ri)  # every factor entry is used exactly once
+        assert np.array_equal(x, x_ref), (name, k)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", CASES + ["ico6"])
+def test_fast_schedule_within_tolerance(name, dtype, oracle_mod, native_lib):
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    b = np.random.default_rng(4).random((p["n"], 7)).astype(dtype)
+    x_ref = oracle_mod.solve(cp, ri, v, perm, b)
+    x, fwd, bwd = oracle_mod.schedule_solve(native_lib, cp, ri, v, perm, b, exact_order=0)
+    assert fwd["n_values"] == len(ri) and bwd["n_values"] == len(ri)
+    assert max_rel_err(x, x_ref) < TOL[np.dtype(dtype)], name
