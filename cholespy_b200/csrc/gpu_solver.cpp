@@ -77,16 +77,17 @@ int padded_rhs(int k) { return (k + 3) & ~3; }  // row stride of the work vector
 
 int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 RHS columns (+ 1 loader warp)
 
-// Rows of the shared-memory row ring: about 32 KB worth, at least two full blocks.
-int sweep_ring_rows(int elem, int k) {
+// Rows of the shared-memory row ring: room for the largest local task plus two full blocks, up to about
+// 92 KB (two CTAs per SM at 128 right-hand sides).
+int sweep_ring_rows(int elem, int k, int local_rows) {
     const int row_bytes = padded_rhs(k) * elem;
-    return std::max(32, std::min(128, (32 << 10) / row_bytes));
+    return std::max(local_rows + 32, std::min(256, (92 << 10) / row_bytes));
 }
 
 // Dynamic shared memory of one sweep CTA (sweep.cuh: struct Smem).
 size_t sweep_smem_bytes(int elem, int k, int local_rows) {
     const size_t row_bytes = (size_t) padded_rhs(k) * (size_t) elem;
-    return kSweepStages * (size_t) page_bytes_for(elem) + ((size_t) sweep_ring_rows(elem, k) + (size_t) local_rows) * row_bytes +
+    return kSweepStages * (size_t) page_bytes_for(elem) + (size_t) sweep_ring_rows(elem, k, local_rows) * row_bytes +
            (2 * kSweepStages + 2 * kSweepRowBars + 2 * kSweepTaskQueue) * 8 + kSweepTaskQueue * 32 + kSweepRowBars * 4;
 }
 
@@ -319,8 +320,8 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
         a.k = k;
         a.epoch = m_epoch;
         a.local_rows = local_rows;
-        a.ring_rows = sweep_ring_rows(m_elem, k);
-        a.reserved = 0;
+        a.ring_rows = sweep_ring_rows(m_elem, k, local_rows);
+        a.src_tma = (((uintptr_t) src & 15) == 0 && ((size_t) k * (size_t) m_elem) % 16 == 0) ? 1 : 0;
         a.slab = (const unsigned char *) s.slab;
         a.tasks = (const SweepTask *) s.tasks;
         a.done = (int *) s.done;

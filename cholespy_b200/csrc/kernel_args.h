@@ -28,9 +28,9 @@ struct SweepArgs {
     int n_tasks;
     int k;
     int epoch;
-    int local_rows;       // largest local task (rows of the shared-memory local area)
-    int ring_rows;        // rows of the shared-memory row ring
-    int reserved;
+    int local_rows;       // largest local task (informational; local tasks live in the row ring)
+    int ring_rows;        // rows of the shared-memory row ring (>= largest local task + 32)
+    int src_tma;          // rows of the user's b can be fetched by TMA (16-byte aligned, 16-byte multiples)
     const unsigned char *slab;
     const SweepTask *tasks;     // ticket-ordered
     int *done;            // per-task epoch flags

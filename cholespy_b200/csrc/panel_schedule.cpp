@@ -321,49 +321,32 @@ struct Builder {
             }
             w.put_bytes(off, idx, 16);
         };
-        if (upper) {
-            // unknowns = columns of p (all wd of them); sources = rows of t present in the block,
-            // visited in DESCENDING row order (reference walks a row of L' from its end backwards)
-            const int wd = S.width(p);
-            const uint32_t tmask = (1u << wd) - 1;
-            const uint32_t wait = local ? 0u : wait_code(task_of_panel[t]);
-            const bool thin = wd <= 3;
-            const int stride = thin ? wd : (wd + 3) & ~3;
-            const size_t off0 = w.record((thin ? REC_BLOCK_D1 : REC_BLOCK_D4) | flag(), S.c0[t], rows | tmask << 16, wait,
-                                         idx_bytes + es * (size_t) nr * (size_t) stride);
-            put_sources(off0, S.c0[t], rows, true);
-            const size_t off = off0 + idx_bytes;
-            for (int s = 0; s < nr; ++s)
-                for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) s * stride + j, buf[nr - 1 - s][j]);
-            img.n_stored_values += (int64_t) nr * stride;
-        } else {
-            // unknowns = rows of t present in the block; sources = all columns of p, ascending
-            (void) P;
-            const int wd = S.width(p);
-            const uint32_t smask = (1u << wd) - 1;
-            const uint32_t wait = local ? 0u : wait_code(task_of_panel[p]);
-            const int stride = (span16(rows) + 3) & ~3;
-            if (2 * nr >= stride) {
-                const size_t off0 = w.record(REC_BLOCK_D4 | flag(), S.c0[p], smask | rows << 16, wait,
-                                             idx_bytes + es * (size_t) wd * (size_t) stride);
-                put_sources(off0, S.c0[p], smask, false);
-                const size_t off = off0 + idx_bytes;
-                for (int j = 0; j < wd; ++j) {
-                    int q = 0;
-                    for (int tt = 0; tt < stride; ++tt)
-                        if (rows >> tt & 1) w.put_value(off, (size_t) j * stride + tt, buf[q++][j]);
-                }
-                img.n_stored_values += (int64_t) wd * stride;
-            } else {
-                const size_t off0 = w.record(REC_BLOCK_TM | flag(), S.c0[p], smask | rows << 16, wait,
-                                             idx_bytes + es * (size_t) nr * (size_t) wd);
-                put_sources(off0, S.c0[p], smask, false);
-                const size_t off = off0 + idx_bytes;
-                for (int r = 0; r < nr; ++r)
-                    for (int j = 0; j < wd; ++j) w.put_value(off, (size_t) r * wd + j, buf[r][j]);
-                img.n_stored_values += (int64_t) nr * wd;
+        // One layout for every block ("grouped source-major"): per source, in sweep order, the values of the
+        // 4-target GROUPS that contain at least one target (zero-filled inside a group).  Explicit zeros
+        // are bit-neutral under fused multiply-subtract.
+        const int wd = S.width(p);
+        const uint32_t tmask = upper ? (1u << wd) - 1 : rows;   // unknowns: columns of p (backward) / rows of t present (forward)
+        const uint32_t smask = upper ? rows : (1u << wd) - 1;   // sources: rows of t present (backward) / columns of p (forward)
+        const int ns = upper ? nr : wd;
+        int group_rank[4], ng = 0;
+        for (int g = 0; g < 4; ++g) group_rank[g] = (tmask >> (4 * g) & 0xf) ? ng++ : -1;
+        const int stride = 4 * ng;
+        const uint32_t wait = local ? 0u : wait_code(task_of_panel[upper ? t : p]);
+        (void) P;
+        const size_t off0 = w.record(REC_BLOCK_D4 | flag(), S.c0[upper ? t : p], smask | tmask << 16, wait,
+                                     idx_bytes + es * (size_t) ns * (size_t) stride);
+        // backward: sources visited in DESCENDING row order (the reference walks a row of L' from its end backwards)
+        put_sources(off0, S.c0[upper ? t : p], smask, upper);
+        const size_t off = off0 + idx_bytes;
+        for (int r = 0; r < ns; ++r) {
+            int q = 0;  // rank of the target among the block's rows (forward)
+            for (int tt = 0; tt < kPanelWidth; ++tt) {
+                if (!(tmask >> tt & 1)) continue;
+                const double v = upper ? buf[nr - 1 - r][tt] : buf[q++][r];
+                w.put_value(off, (size_t) r * stride + 4 * group_rank[tt >> 2] + (tt & 3), v);
             }
         }
+        img.n_stored_values += (int64_t) ns * stride;
     }
 
     // Fast mode: the triangle as a dense wp x wp matrix (wp = 1 or round4(w)) in pivot order with

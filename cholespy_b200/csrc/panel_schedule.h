@@ -55,10 +55,10 @@ enum RecordType : uint32_t {
     REC_BEGIN_ZERO = 2,  // a = row0, b = w.  tile = 0
     REC_BEGIN_SLOT = 3,  // a = row0, b = w | slot << 8, c = wait + 1.  tile = scratch slot (chained partial sums)
     REC_ADD_SLOT = 4,    // b = slot << 8, c = wait + 1.  tile += scratch slot
-    REC_BLOCK_D4 = 5,    // a = src_row0, b = smask | tmask << 16, c = wait + 1.  source-major values, target
-                         // stride = round4(highest target + 1), zero-filled where a target is absent
-    REC_BLOCK_D1 = 6,    // same header; targets are the prefix 0..nt-1 (nt <= 3), stride nt, no padding
-    REC_BLOCK_TM = 7,    // same header; target-major values [target rank][source rank], no padding
+    REC_BLOCK_D4 = 5,    // a = src_row0, b = smask | tmask << 16, c = wait + 1.  "grouped source-major" values: per source
+                         // (sweep order) 4 values for every 4-target group that holds a target, zero-filled inside
+    REC_BLOCK_D1 = 6,    // (retired layouts, never emitted)
+    REC_BLOCK_TM = 7,
     REC_END_FINAL = 8,   // a = row0, b = w.  payload: triangle in sweep order (+ perm[16] backward); solve, store, publish
     REC_END_SLOT = 9,    // b = slot << 8.  park the tile in a scratch slot
     REC_END_DENSE = 10,  // a = row0, b = w.  like END_FINAL with the triangle as a dense wp x wp matrix (wp = 1 or

@@ -25,9 +25,10 @@
 //     conflict-free), and hand the ring rows back through an "empty" mbarrier;
 //   * the tile (<= 16 rows) of the panel being solved lives in registers, one RHS column per lane;
 //   * LOCAL tasks (complete subtrees of small panels, most of the rows): the subtree's right-hand
-//     side rows and the external rows it reads are gathered into shared memory once (one batch of
-//     independent loads), every record then works out of shared memory, and the solved rows are
-//     written back once -- no per-row round trips to L2;
+//     side rows and the external rows it reads are staged into the row ring by the loader as ONE
+//     record (while the compute warps are still busy with earlier tasks), every record of the task
+//     then works in place in shared memory, and the solved rows are written back once -- no
+//     per-row round trips to L2;
 //   * dependencies: one epoch-valued ready flag per TASK (ld.acquire.gpu / st.release.gpu after a
 //     named barrier of the compute warps); flags are never cleared (the epoch is the solve counter);
 //   * the work vector `tmp` and the partial-tile scratch have their row stride padded to 4 elements
@@ -161,46 +162,43 @@ template <> struct Vec4<double> {
     }
 };
 
-// Substitution with the panel's triangle given as a dense WP x WP matrix with reciprocal pivots
-// (REC_END_DENSE): fully static, one row of WP values per pivot from shared memory.
-template <typename F, bool UPPER, int WP>
-__device__ __forceinline__ void tri_dense(F (&T)[W], const F *m) {
+// Substitution with the panel's triangle given as a dense wp x wp matrix (wp = 1 or a multiple of 4) with
+// reciprocal pivots (REC_END_DENSE).  One copy of the code for every width (the instruction footprint
+// of these kernels matters: L0 holds ~6 KB of SASS, L1.5 32 KB): the pivot loop is unrolled over all
+// 16 steps so the tile stays in registers, steps and 4-value groups beyond wp are skipped by
+// warp-uniform branches.
+template <typename F, bool UPPER>
+__device__ __forceinline__ void tri_dense(F (&T)[W], const F *m, int wp) {
 #pragma unroll
-    for (int step = 0; step < WP; ++step) {
-        const int s = UPPER ? WP - 1 - step : step;
-        F row[WP];
-        if constexpr (WP == 1) {
-            row[0] = m[0];
-        } else {
+    for (int step = 0; step < W; ++step) {
+        const int s = UPPER ? W - 1 - step : step;
+        if (s < wp) {
+            const F *row = m + s * wp;
+            T[s] = T[s] * row[s];
 #pragma unroll
-            for (int q = 0; q < WP / 4; ++q) {
-                const Vec4<F> vv = Vec4<F>::load(m + s * WP + 4 * q);
+            for (int q = 0; q < W / 4; ++q) {
+                const bool needed = UPPER ? 4 * q < s : 4 * q + 3 > s;  // the group holds an unknown still to update
+                if (needed && 4 * q < wp) {
+                    const Vec4<F> vv = Vec4<F>::load(row + 4 * q);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) row[4 * q + j] = vv.x[j];
+                    for (int j = 0; j < 4; ++j) {
+                        const int t = 4 * q + j;
+                        if (UPPER ? t < s : t > s) T[t] = fnma(vv.x[j], T[s], T[t]);
+                    }
+                }
             }
         }
-        T[s] = T[s] * row[s];
-#pragma unroll
-        for (int t = UPPER ? 0 : s + 1; t < (UPPER ? s : WP); ++t) T[t] = fnma(row[t], T[s], T[t]);
     }
 }
 
-__device__ __forceinline__ bool is_staged_block(uint32_t h0) {  // a block record outside a local task
-    const uint32_t type = h0 & 0xff;
-    return type >= REC_BLOCK_D4 && type <= REC_BLOCK_TM;
-}
-// index (bit position) of the r-th source of a mask in sweep order (ascending forward, descending backward)
-__device__ __forceinline__ int nth_source(uint32_t mask, int r, bool upper) {
-    if (upper) mask = __brev(mask) >> 16;  // 16-bit masks
-    const int pos = __fns(mask, 0, r + 1);
-    return upper ? 15 - pos : pos;
-}
 __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 // Spin loops trap instead of hanging the GPU if a dependency never arrives (a schedule or kernel bug).
 #define SWEEP_SPIN_GUARD(counter)            \
     if (++(counter) > (1u << 27)) __trap();
+
+__device__ __forceinline__ int wrap(int r, int n) { return r >= n ? r - n : r; }
 
 // A task descriptor in the CTA's shared-memory task queue (loader -> compute warps).
 struct QueuedTask {
@@ -212,87 +210,75 @@ struct QueuedTask {
     unsigned long long pad2;
 };
 
-// One block record: tile -= L_block * sources.  Source row r (sweep order) is row (base + r) mod ring_rows
-// of the row ring (STAGED), or row idx[r] of the local area (LOCAL; idx = 16 bytes in front of the values).
-// `rows` points at this lane's column of row 0; rows are kp elements apart.
-template <typename F, bool LOCAL>
-__device__ __forceinline__ void run_block(F (&T)[W], uint32_t type, uint32_t masks, const unsigned char *pay, const F *rows,
-                                          int kp, int base, int ring_rows) {
-    const uint32_t tmask = masks >> 16, smask = masks & 0xffff;
-    const unsigned char *idx = pay;
+// One block record: tile -= L_block * sources ("grouped source-major" values, panel_schedule.h).  `ring`
+// points at this lane's column of ring row 0 (rows are kp elements apart, the ring has ring_rows rows).
+// The record's rows start at ring row `base`:
+//   STAGED: the ns source rows in ASCENDING row order (the backward sweep visits them descending);
+//   LOCAL:  the rows of the whole local task; idx (16 bytes in front of the values) = local index per source.
+// A plain loop on purpose (small instruction footprint); two sources per iteration hide the LDS latency.
+template <typename F, bool LOCAL, bool UPPER>
+__device__ __forceinline__ void run_block(F (&T)[W], uint32_t masks, const unsigned char *pay, const F *ring, int kp, int base,
+                                          int ring_rows) {
+    const uint32_t tmask = masks >> 16;
+    const int ns = __popc(masks & 0xffff);
+    const bool g0 = (tmask & 0x000f) != 0, g1 = (tmask & 0x00f0) != 0, g2 = (tmask & 0x0f00) != 0, g3 = (tmask & 0xf000) != 0;
+    const int stride = 4 * ((int) g0 + (int) g1 + (int) g2 + (int) g3);
     const F *val = reinterpret_cast<const F *>(pay + (LOCAL ? 16 : 0));
-    const int ns = __popc(smask);
-    auto source = [&](int r) -> F {
-        if (LOCAL) return rows[(int) idx[r] * kp];
-        int q = base + r;
-        if (q >= ring_rows) q -= ring_rows;
-        return rows[q * kp];
-    };
-    if (type == REC_BLOCK_D4) {
-        const int stride = (32 - __clz(tmask) + 3) & ~3;
-        if (stride == 16) {
+    int pos = UPPER ? wrap(base + ns - 1, ring_rows) : base;
 #pragma unroll 2
-            for (int r = 0; r < ns; ++r) {
-                const F x = source(r);
-                const F *vr = val + r * 16;
-#pragma unroll
-                for (int t4 = 0; t4 < 4; ++t4) {
-                    const Vec4<F> vv = Vec4<F>::load(vr + t4 * 4);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) T[t4 * 4 + j] = fnma(vv.x[j], x, T[t4 * 4 + j]);
-                }
-            }
+    for (int r = 0; r < ns; ++r) {
+        int row;
+        if (LOCAL) {
+            row = wrap(base + (int) pay[r], ring_rows);
         } else {
-            for (int r = 0; r < ns; ++r) {
-                const F x = source(r);
-                const F *vr = val + r * stride;
-#pragma unroll
-                for (int t4 = 0; t4 < 3; ++t4) {
-                    if (t4 * 4 < stride) {
-                        const Vec4<F> vv = Vec4<F>::load(vr + t4 * 4);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) T[t4 * 4 + j] = fnma(vv.x[j], x, T[t4 * 4 + j]);
-                    }
-                }
-            }
+            row = pos;
+            if (UPPER) pos = pos == 0 ? ring_rows - 1 : pos - 1;
+            else pos = pos + 1 == ring_rows ? 0 : pos + 1;
         }
-    } else if (type == REC_BLOCK_D1) {
-        const int nt = __popc(tmask);
-        for (int r = 0; r < ns; ++r) {
-            const F x = source(r);
-            const F *vr = val + r * nt;
+        const F x = ring[(size_t) row * kp];
+        const F *v = val;
+        if (g0) {
+            const Vec4<F> vv = Vec4<F>::load(v);
+            v += 4;
 #pragma unroll
-            for (int t = 0; t < 3; ++t)
-                if (t < nt) T[t] = fnma(vr[t], x, T[t]);
+            for (int j = 0; j < 4; ++j) T[j] = fnma(vv.x[j], x, T[j]);
         }
-    } else {  // REC_BLOCK_TM: target-major, arbitrary target set
-        uint32_t tm = tmask;
-        while (tm) {
-            const int t = __ffs(tm) - 1;
-            tm &= tm - 1;
-            F acc = get_row<F>(T, t);
-            for (int r = 0; r < ns; ++r) acc = fnma(val[r], source(r), acc);
-            val += ns;
-            put_row<F>(T, t, acc);
+        if (g1) {
+            const Vec4<F> vv = Vec4<F>::load(v);
+            v += 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) T[4 + j] = fnma(vv.x[j], x, T[4 + j]);
         }
+        if (g2) {
+            const Vec4<F> vv = Vec4<F>::load(v);
+            v += 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) T[8 + j] = fnma(vv.x[j], x, T[8 + j]);
+        }
+        if (g3) {
+            const Vec4<F> vv = Vec4<F>::load(v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) T[12 + j] = fnma(vv.x[j], x, T[12 + j]);
+        }
+        val += stride;
     }
 }
 
-// Records whose input rows the LOADER stages into the row ring (everything else is handled by the
-// compute warps alone).  Returns the number of rows, 0 if the record is not staged.
-template <bool UPPER>
+// Records whose input rows the LOADER stages into the row ring.  Returns the number of rows, 0 if the
+// record needs no rows (those are handled by the compute warps alone).
 __device__ __forceinline__ int staged_rows(const uint4 &h) {
-    const uint32_t type = h.x & 0xff;  // local records carry REC_LOCAL_FLAG and never match
-    if (type >= REC_BLOCK_D4 && type <= REC_BLOCK_TM) return __popc(h.z & 0xffff);
+    const uint32_t type = h.x & 0xff;  // records inside local tasks carry REC_LOCAL_FLAG and never match
+    if (type == REC_BLOCK_D4) return __popc(h.z & 0xffff);
     if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) return W;
-    if (UPPER && type == REC_BEGIN_RHS) return (int) h.z;
+    if (type == REC_BEGIN_RHS) return (int) h.z;
+    if (type == REC_LOCAL_LOAD) return (int) (h.z & 0xffff) + (int) (h.z >> 16);
     return 0;
 }
 
 // Shared memory of one CTA (dynamic):
 //   [kStages][kPage]          slab ring (TMA destination)
-//   [ring_rows][kp]           row ring: already-solved rows / partial tiles staged by the loader
-//   [local_rows][kp]          local area: the rows of the local task being solved
+//   [ring_rows][kp]           row ring: right-hand-side rows, already-solved rows, partial tiles and the
+//                             rows of local tasks, all staged by the loader
 //   full[kStages], empty[kStages]      slab ring barriers   (empty: compute warps + loader)
 //   rfull[kRowBars], rempty[kRowBars]  row ring barriers    (rempty: compute warps)
 //   tfull[kTaskQueue], tempty[kTaskQueue]
@@ -301,15 +287,13 @@ template <typename F>
 struct Smem {
     unsigned char *slab;
     F *ring;
-    F *area;
     uint64_t *full, *empty, *rfull, *rempty, *tfull, *tempty;
     QueuedTask *queue;
     int *rows_of;
-    __device__ __forceinline__ Smem(unsigned char *raw, int kp, int ring_rows, int local_rows) {
+    __device__ __forceinline__ Smem(unsigned char *raw, int kp, int ring_rows) {
         slab = raw;
         ring = reinterpret_cast<F *>(raw + (size_t) kStages * kPage);
-        area = ring + (size_t) ring_rows * kp;
-        full = reinterpret_cast<uint64_t *>(area + (size_t) local_rows * kp);
+        full = reinterpret_cast<uint64_t *>(ring + (size_t) ring_rows * kp);
         empty = full + kStages;
         rfull = empty + kStages;
         rempty = rfull + kRowBars;
@@ -322,21 +306,49 @@ struct Smem {
 
 // ---- the loader warp -------------------------------------------------------------------------------
 // Draws tickets, streams each task's slab into the page ring, and for every staged record (in order)
-// polls the ready flag of its producer and copies its input rows into the row ring with 1-D TMA bulk
-// copies completing on that record's mbarrier.  Runs ahead of the compute warps by up to the depth of
-// the three rings, across task boundaries.
+// polls the ready flag(s) of its producer(s) and copies its input rows into the row ring with 1-D TMA
+// bulk copies completing on that record's mbarrier (runs of consecutive rows are one copy).  It is the
+// only warp that reads the right-hand side, the work vector or the scratch tiles from global memory,
+// and it runs ahead of the compute warps by up to the depth of the three rings, across task boundaries.
 template <typename F, bool UPPER>
-__device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F> &sm, int lane, int n_compute) {
+__device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F> &sm, int lane) {
     const int k = a.k, kp = (k + 3) & ~3;
     const int ring_rows = a.ring_rows;
     const uint32_t row_bytes = (uint32_t) kp * (uint32_t) sizeof(F);
+    const uint32_t src_row_bytes = (uint32_t) k * (uint32_t) sizeof(F);
+    const bool src_tma = a.src_tma != 0;  // rows of b are 16-byte aligned multiples of 16 bytes
     const int epoch = a.epoch;
     uint32_t gpage = 0;       // global index of the current task's first page
     uint32_t issued = 0;      // pages handed to TMA so far (lane 0 only)
     uint32_t j_issue = 0;     // staged records issued so far == sequence number of the next one
-    uint32_t rows_issued = 0, rows_released = 0, j_rel = 0;
+    uint32_t j_rel = 0;       // staged records known to be released by the compute warps
+    int rows_in_flight = 0;   // ring rows of records j_rel .. j_issue - 1
+    int head = 0;             // ring row the next record starts at
     int t_next = 0;
     if (lane == 0) t_next = atomicAdd(a.ticket, 1);
+
+    // n consecutive rows (row_bytes each, contiguous in global memory) -> ring rows slot, slot + 1, ...
+    auto copy_rows = [&](int slot, const F *src, int n, uint64_t *bar) {
+        const int first = min(n, ring_rows - slot);
+        tma_load_1d(sm.ring + (size_t) slot * kp, src, (uint32_t) first * row_bytes, bar);
+        if (n > first) tma_load_1d(sm.ring, src + (size_t) first * kp, (uint32_t) (n - first) * row_bytes, bar);
+    };
+    // rows b[perm[i]], i < n -> ring rows head + i (forward sweep only); returns the TMA bytes to expect
+    auto copy_rhs_rows = [&](const int *perm, int n) -> uint32_t {
+        if (src_tma) {
+            for (int i = lane; i < n; i += 32)
+                tma_load_1d(sm.ring + (size_t) wrap(head + i, ring_rows) * kp, a.src + (size_t) perm[i] * k, src_row_bytes,
+                            sm.rfull + j_issue % kRowBars);
+            return (uint32_t) n * src_row_bytes;
+        }
+        const int total = n * k;
+#pragma unroll 1
+        for (int e = lane; e < total; e += 32) {
+            const int i = e / k, c = e - i * k;
+            sm.ring[(size_t) wrap(head + i, ring_rows) * kp + c] = __ldg(a.src + (size_t) perm[i] * k + c);
+        }
+        return 0u;
+    };
 
     for (uint32_t q = 0;; ++q) {
         // ---- next task descriptor -> queue --------------------------------------------------------
@@ -384,25 +396,45 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
             const unsigned char *p = sm.slab + (size_t) stage * kPage;
             const unsigned char *pend = p + min((uint32_t) kPage, total - pg * kPage);
             while (p < pend) {
-                // scan: the next (up to 32) staged records of this page; lane i keeps record i
+                // scan: the next (up to 32) staged records of this page; lane i keeps record i.  A record with
+                // several producers (the backward LOCAL_LOAD) is handled alone.
                 int n = 0;
                 uint32_t my_off = 0, my_code = 0;
+                bool multi = false;
                 const unsigned char *qp = p;
                 while (qp < pend && n < 32) {
                     const uint4 hq = *reinterpret_cast<const uint4 *>(qp);
-                    if (staged_rows<UPPER>(hq) > 0) {
+                    if (staged_rows(hq) > 0) {
+                        const uint32_t tq = hq.x & 0xff;
+                        const bool many = tq == REC_LOCAL_LOAD && hq.w != 0;
+                        if (many && n > 0) break;
                         if (lane == n) {
                             my_off = (uint32_t) (qp - p);
-                            my_code = (hq.x & 0xff) == REC_BEGIN_RHS ? 0u : hq.w;
+                            my_code = (tq == REC_BEGIN_RHS || tq == REC_LOCAL_LOAD) ? 0u : hq.w;
                         }
                         n += 1;
+                        if (many) {
+                            multi = true;
+                            break;
+                        }
                     }
                     qp += (hq.x >> 8) * 16;
                 }
                 if (n == 0) break;  // nothing left to stage in this page
-                // poll: one flag per lane, the ready prefix goes now
-                int n_go;
-                {
+                int n_go = n;
+                if (multi) {
+                    // every producer of the local task's external rows must have published
+                    const uint4 h = *reinterpret_cast<const uint4 *>(p + __shfl_sync(kFullMask, my_off, 0));
+                    const int n_ext = (int) (h.z >> 16), n_wait = (int) h.w;
+                    const int *waits = reinterpret_cast<const int *>(p + __shfl_sync(kFullMask, my_off, 0) + 16) + ((n_ext + 3) & ~3);
+                    for (int e = lane; e < n_wait; e += 32) {
+                        const int *flag = a.done + (waits[e] - 1);
+                        unsigned spins = 0;
+                        while (ld_acquire_gpu(flag) != epoch) { SWEEP_SPIN_GUARD(spins) }
+                    }
+                    __syncwarp();
+                } else {
+                    // poll: one flag per lane, the ready prefix goes now
                     unsigned spins = 0;
                     for (;;) {
                         bool ready = true;
@@ -418,30 +450,55 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     const unsigned char *rec = p + __shfl_sync(kFullMask, my_off, i);
                     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
                     const uint32_t type = h.x & 0xff;
-                    const int nr = staged_rows<UPPER>(h);
+                    const int nr = staged_rows(h);
                     // back-pressure: a free barrier pair and nr free rows in the ring
-                    while (j_issue - j_rel >= (uint32_t) kRowBars || rows_issued + (uint32_t) nr - rows_released > (uint32_t) ring_rows) {
+                    while (j_issue - j_rel >= (uint32_t) kRowBars || rows_in_flight + nr > ring_rows) {
                         mbar_wait(sm.rempty + j_rel % kRowBars, (j_rel / kRowBars) & 1);
-                        rows_released += (uint32_t) sm.rows_of[j_rel % kRowBars];
+                        rows_in_flight -= sm.rows_of[j_rel % kRowBars];
                         j_rel += 1;
                     }
                     __syncwarp();
                     uint64_t *bar = sm.rfull + j_issue % kRowBars;
-                    if (lane == 0) {
-                        sm.rows_of[j_issue % kRowBars] = nr;
-                        mbar_expect_tx(bar, (uint32_t) nr * row_bytes);
+                    if (lane == 0) sm.rows_of[j_issue % kRowBars] = nr;
+                    uint32_t tx = (uint32_t) nr * row_bytes;
+                    if (type == REC_BLOCK_D4) {
+                        // runs of consecutive source rows, ascending: lane r copies run r
+                        uint32_t m = h.z & 0xffff;
+                        int rank = 0, n_runs = 0, my_start = 0, my_len = 0, my_rank = 0;
+                        while (m) {
+                            const int s = __ffs(m) - 1;
+                            const int len = __ffs(~(m >> s)) - 1;
+                            if (lane == n_runs) my_start = s, my_len = len, my_rank = rank;
+                            rank += len;
+                            m &= ~(((1u << len) - 1u) << s);
+                            n_runs += 1;
+                        }
+                        if (lane < n_runs)
+                            copy_rows(wrap(head + my_rank, ring_rows), a.tmp + (size_t) ((int) h.y + my_start) * kp, my_len, bar);
+                    } else if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) {
+                        if (lane == 0) copy_rows(head, a.scratch + (size_t) (h.z >> 8) * W * kp, W, bar);
+                    } else if (type == REC_BEGIN_RHS) {
+                        if (UPPER) {
+                            if (lane == 0) copy_rows(head, a.tmp + (size_t) (int) h.y * kp, nr, bar);
+                        } else {
+                            tx = copy_rhs_rows(reinterpret_cast<const int *>(rec + 16), nr);
+                        }
+                    } else {  // REC_LOCAL_LOAD
+                        const int n_int = (int) (h.z & 0xffff), n_ext = (int) (h.z >> 16);
+                        const int *list = reinterpret_cast<const int *>(rec + 16);
+                        if (UPPER) {
+                            if (lane == 0) copy_rows(head, a.tmp + (size_t) (int) h.y * kp, n_int, bar);
+                            for (int e = lane; e < n_ext; e += 32)
+                                copy_rows(wrap(head + n_int + e, ring_rows), a.tmp + (size_t) list[e] * kp, 1, bar);
+                        } else {
+                            tx = copy_rhs_rows(list, n_int);
+                        }
                     }
-                    if (lane < nr) {
-                        const F *src;
-                        if (type == REC_BEGIN_RHS) src = a.tmp + (size_t) ((int) h.y + lane) * kp;
-                        else if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) src = a.scratch + ((size_t) (h.z >> 8) * W + lane) * kp;
-                        else src = a.tmp + (size_t) ((int) h.y + nth_source(h.z & 0xffff, lane, UPPER)) * kp;
-                        const uint32_t slot = (rows_issued + (uint32_t) lane) % (uint32_t) ring_rows;
-                        tma_load_1d(sm.ring + (size_t) slot * kp, src, row_bytes, bar);
-                    }
-                    __syncwarp();
+                    __syncwarp();  // manual copies (unaligned right-hand side) are complete before the arrival
+                    if (lane == 0) mbar_expect_tx(bar, tx);
                     j_issue += 1;
-                    rows_issued += (uint32_t) nr;
+                    rows_in_flight += nr;
+                    head = wrap(head + nr, ring_rows);
                     last = rec + (h.x >> 8) * 16;
                 }
                 p = last;
@@ -460,17 +517,13 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
     const int ring_rows = a.ring_rows;
     const int col = warp * 32 + lane;
     const bool active = col < k;
-    const int kw = min(32, k - warp * 32);                        // columns owned by this warp
-    const int chunks = ((kw + 3) & ~3) * (int) sizeof(F) / 16;    // 16-byte chunks of this warp's row segment
-    const int lcol = active ? col : warp * 32;                    // a column this lane may always read
-    const F *ring = sm.ring + lcol;
-    F *area = sm.area + lcol;
-    const int epoch = a.epoch;
+    const int lcol = active ? col : warp * 32;   // a column this lane may always read
+    F *ring = sm.ring + lcol;                    // this lane's column of ring row 0
     const bool leader = warp == 0 && lane == 0;
 
     uint32_t gpage = 0;      // global index of the current task's first page
     uint32_t j = 0;          // sequence number of the next staged record
-    uint32_t rows_seen = 0;  // rows of all staged records so far (ring position of the next one)
+    int head = 0;            // ring row the next staged record starts at
     F T[W];
     long long wait_cycles = 0;  // tracing only
 
@@ -486,25 +539,22 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
             wait_cycles = 0;
         }
 
-        int row0 = 0, w = 0;   // the panel whose tile is in registers (row0: global row, or local index)
+        int row0 = 0, w = 0;        // the panel whose tile is in registers (row0: global row, or local index)
+        int lbase = 0, lrows = 0;   // ring rows of the local task being solved
         // waits for the loader to have staged the next record's rows; returns their ring position
         auto acquire_rows = [&]() {
             const long long c0 = a.trace ? clock64() : 0;
             mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1);
             if (a.trace) wait_cycles += clock64() - c0;
-            return (int) (rows_seen % (uint32_t) ring_rows);
+            return head;
         };
         auto release_rows = [&](int nr) {
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.rempty + j % kRowBars);
             j += 1;
-            rows_seen += (uint32_t) nr;
+            head = wrap(head + nr, ring_rows);
         };
-        auto ring_row = [&](int base, int i) -> F {
-            int r = base + i;
-            if (r >= ring_rows) r -= ring_rows;
-            return ring[(size_t) r * kp];
-        };
+        auto ring_at = [&](int base, int i) -> F & { return ring[(size_t) wrap(base + i, ring_rows) * kp]; };
         // tile -> tmp rows (and, backward, -> x through P')
         auto store_tile = [&](const int *perm) {
 #pragma unroll
@@ -532,13 +582,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                 }
             }
         };
-        auto tri_fast = [&](const F *m) {
-            if (w == 1) tri_dense<F, UPPER, 1>(T, m);
-            else if (w <= 4) tri_dense<F, UPPER, 4>(T, m);
-            else if (w <= 8) tri_dense<F, UPPER, 8>(T, m);
-            else if (w <= 12) tri_dense<F, UPPER, 12>(T, m);
-            else tri_dense<F, UPPER, 16>(T, m);
-        };
+        auto tri_fast = [&](const F *m) { tri_dense<F, UPPER>(T, m, w == 1 ? 1 : (w + 3) & ~3); };
 
         for (uint32_t pg = 0; pg < n_pages; ++pg) {
             const uint32_t g = gpage + pg, stage = g % kStages;
@@ -551,12 +595,12 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                 const bool local = (h.x & REC_LOCAL_FLAG) != 0;
                 const unsigned char *pay = p + 16;
                 p += (h.x >> 8) * 16;
-                if (type >= REC_BLOCK_D4 && type <= REC_BLOCK_TM) {
+                if (type == REC_BLOCK_D4) {
                     if (local) {
-                        run_block<F, true>(T, type, h.z, pay, area, kp, 0, 0);
+                        run_block<F, true, UPPER>(T, h.z, pay, ring, kp, lbase, ring_rows);
                     } else {
                         const int base = acquire_rows();
-                        run_block<F, false>(T, type, h.z, pay, ring, kp, base, ring_rows);
+                        run_block<F, false, UPPER>(T, h.z, pay, ring, kp, base, ring_rows);
                         release_rows(__popc(h.z & 0xffff));
                     }
                 } else if (type == REC_BEGIN_RHS) {
@@ -564,16 +608,12 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                     w = (int) h.z;
                     if (local) {
 #pragma unroll
-                        for (int i = 0; i < W; ++i) T[i] = i < w ? area[(size_t) (row0 + i) * kp] : F(0);
-                    } else if (UPPER) {
+                        for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(lbase, row0 + i) : F(0);
+                    } else {
                         const int base = acquire_rows();
 #pragma unroll
-                        for (int i = 0; i < W; ++i) T[i] = i < w ? ring_row(base, i) : F(0);
+                        for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(base, i) : F(0);
                         release_rows(w);
-                    } else {
-                        const int *perm = reinterpret_cast<const int *>(pay);
-#pragma unroll
-                        for (int i = 0; i < W; ++i) T[i] = (i < w && active) ? __ldg(a.src + (size_t) perm[i] * k + col) : F(0);
                     }
                 } else if (type == REC_END_DENSE || type == REC_END_FINAL) {
                     const int *perm = reinterpret_cast<const int *>(pay);
@@ -583,60 +623,25 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         if (active) {
 #pragma unroll
                             for (int i = 0; i < W; ++i)
-                                if (i < w) area[(size_t) (row0 + i) * kp] = T[i];
+                                if (i < w) ring_at(lbase, row0 + i) = T[i];
                         }
                     } else {
                         store_tile(perm);
                     }
                 } else if (type == REC_LOCAL_LOAD) {
-                    const int lo = (int) h.y, n_int = (int) (h.z & 0xffff), n_ext = (int) (h.z >> 16), n_wait = (int) h.w;
-                    const int *list = reinterpret_cast<const int *>(pay);
-                    if (!UPPER) {
-                        // area[i] = b[perm[i]]: independent loads, 8 in flight per lane
-                        if (active) {
-                            for (int i0 = 0; i0 < n_int; i0 += 8) {
-                                F v[8];
-#pragma unroll
-                                for (int jj = 0; jj < 8; ++jj)
-                                    v[jj] = i0 + jj < n_int ? __ldg(a.src + (size_t) list[i0 + jj] * k + col) : F(0);
-#pragma unroll
-                                for (int jj = 0; jj < 8; ++jj)
-                                    if (i0 + jj < n_int) area[(size_t) (i0 + jj) * kp] = v[jj];
-                            }
-                        }
-                    } else {
-                        const int *waits = list + ((n_ext + 3) & ~3);
-                        const long long c0 = a.trace ? clock64() : 0;
-                        for (int e = lane; e < n_wait; e += 32) {
-                            const int *flag = a.done + (waits[e] - 1);
-                            unsigned spins = 0;
-                            while (ld_acquire_gpu(flag) != epoch) { SWEEP_SPIN_GUARD(spins) }
-                        }
-                        __syncwarp();
-                        if (a.trace) wait_cycles += clock64() - c0;
-                        const int n_rows = n_int + n_ext;
-                        F *dst0 = sm.area + warp * 32;
-                        const F *src0 = a.tmp + warp * 32;
-                        for (int e = lane; e < n_rows * chunks; e += 32) {
-                            const int r = e / chunks, c = e - r * chunks;
-                            const int grow = r < n_int ? lo + r : list[r - n_int];
-                            cp_async_16(reinterpret_cast<unsigned char *>(dst0 + (size_t) r * kp) + 16 * c,
-                                        reinterpret_cast<const unsigned char *>(src0 + (size_t) grow * kp) + 16 * c);
-                        }
-                        cp_async_commit();
-                        cp_async_wait<0>();
-                        __syncwarp();
-                    }
+                    lrows = (int) (h.z & 0xffff) + (int) (h.z >> 16);
+                    lbase = acquire_rows();   // held until LOCAL_STORE
                 } else if (type == REC_LOCAL_STORE) {
                     const int lo = (int) h.y, n_int = (int) h.z;
                     const int *perm = reinterpret_cast<const int *>(pay);
                     if (active) {
                         for (int i = 0; i < n_int; ++i) {
-                            const F v = area[(size_t) i * kp];
+                            const F v = ring_at(lbase, i);
                             __stcg(a.tmp + (size_t) (lo + i) * kp + col, v);
                             if (UPPER) a.dst[(size_t) perm[i] * k + col] = v;
                         }
                     }
+                    release_rows(lrows);
                 } else if (type == REC_BEGIN_ZERO) {
                     row0 = (int) h.y;
                     w = (int) h.z;
@@ -650,7 +655,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                     const int base = acquire_rows();
 #pragma unroll
                     for (int i = 0; i < W; ++i) {
-                        const F val = ring_row(base, i);
+                        const F val = ring_at(base, i);
                         T[i] = type == REC_BEGIN_SLOT ? val : T[i] + val;
                     }
                     release_rows(W);
@@ -675,7 +680,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                 a.trace[8 * (size_t) task + 2] = global_ns();
                 a.trace[8 * (size_t) task + 3] = (unsigned long long) wait_cycles;
             }
-            st_release_gpu(a.done + task, epoch);
+            st_release_gpu(a.done + task, a.epoch);
             mbar_arrive(sm.tempty + q % kTaskQueue);
         }
     }
@@ -688,7 +693,7 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
     const int warp = threadIdx.x >> 5;
     const int n_compute = (blockDim.x >> 5) - 1;  // the last warp is the loader
     const int kp = (a.k + 3) & ~3;
-    const Smem<F> sm(smem_raw, kp, a.ring_rows, a.local_rows);
+    const Smem<F> sm(smem_raw, kp, a.ring_rows);
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) *a.ticket_next = 0;
 #pragma unroll
@@ -710,14 +715,14 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (warp == n_compute) loader_warp<F, UPPER>(a, sm, lane, n_compute);
+    if (warp == n_compute) loader_warp<F, UPPER>(a, sm, lane);
     else compute_warp<F, UPPER>(a, sm, warp, lane, n_compute);
 }
 
 }  // namespace sweep
 
 #define CHB_SWEEP(NAME, T, UP)                                                                 \
-    extern "C" __global__ void __launch_bounds__(160) NAME(const chb::SweepArgs<T> a) {          \
+    extern "C" __global__ void __launch_bounds__(160, 2) NAME(const chb::SweepArgs<T> a) {          \
         sweep::sweep_worker<T, UP>(a);                                                         \
     }
 

@@ -122,39 +122,23 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                     const F *s = scratch + (size_t) (h[2] >> 8) * W * k;
                     for (size_t i = 0; i < (size_t) W * k; ++i) acc[i] += s[i];
                 } break;
-                case BLOCK_D4:
-                case BLOCK_D1: {
+                case BLOCK_D4: {
                     if (!waited(h[3])) return -4;
                     const int src0 = (int) h[1];
                     const uint32_t smask = h[2] & 0xffff, tmask = h[2] >> 16;
-                    const int stride = type == BLOCK_D4 ? (span16(tmask) + 3) & ~3 : __builtin_popcount(tmask);
+                    int group_rank[4], ng = 0;
+                    for (int g = 0; g < 4; ++g) group_rank[g] = (tmask >> (4 * g) & 0xf) ? ng++ : -1;
+                    const int stride = 4 * ng;
                     int r = 0;
                     for (int bit = 0; bit < W; ++bit) {
                         const int s = upper ? W - 1 - bit : bit;
                         if (!(smask >> s & 1)) continue;
                         const F *srow = source_row(src0, s, r);
                         if (!srow) return -7;
-                        for (int t = 0; t < stride; ++t)
-                            for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(v[(size_t) r * stride + t], srow[c], acc[(size_t) t * k + c]);
-                        ++r;
-                    }
-                } break;
-                case BLOCK_TM: {
-                    if (!waited(h[3])) return -4;
-                    const int src0 = (int) h[1];
-                    const uint32_t smask = h[2] & 0xffff, tmask = h[2] >> 16;
-                    const int ns = __builtin_popcount(smask);
-                    int r = 0;
-                    for (int t = 0; t < W; ++t) {
-                        if (!(tmask >> t & 1)) continue;
-                        int sr = 0;
-                        for (int bit = 0; bit < W; ++bit) {
-                            const int s = upper ? W - 1 - bit : bit;
-                            if (!(smask >> s & 1)) continue;
-                            const F *srow = source_row(src0, s, sr);
-                            if (!srow) return -7;
-                            for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(v[(size_t) r * ns + sr], srow[c], acc[(size_t) t * k + c]);
-                            ++sr;
+                        for (int t = 0; t < W; ++t) {
+                            if (!(tmask >> t & 1)) continue;
+                            const F l = v[(size_t) r * stride + 4 * group_rank[t >> 2] + (t & 3)];
+                            for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] = fnma(l, srow[c], acc[(size_t) t * k + c]);
                         }
                         ++r;
                     }

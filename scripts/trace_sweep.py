@@ -46,6 +46,22 @@ def main():
         res[key] = buf.reshape(nt, 8)
         t0 = res[key][:, 0].min()
         print(key, "tasks", nt, "span %.3f ms" % ((res[key][:, 2].max() - t0) / 1e6), flush=True)
+    # the task table of the same (deterministic) schedule, built on the host: bytes, level, first record type
+    hs = ctypes.c_void_p()
+    _capi.check(lib.chb_schedule_create(ctypes.byref(hs), _capi.F32 if dt == "f" else _capi.F64, len(perm), len(ri), cp.ctypes.data,
+                                        ri.ctypes.data, v.ctypes.data, perm.ctypes.data, -1))
+    for upper, key in ((0, "fwd"), (1, "bwd")):
+        slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        sinfo = (ctypes.c_int64 * 10)()
+        lib.chb_schedule_sweep(hs, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), sinfo, 10)
+        nt = int(sinfo[0])
+        td = np.ctypeslib.as_array(ctypes.cast(tasks, ctypes.POINTER(ctypes.c_uint32)), shape=(nt, 4)).copy()
+        sl = np.ctypeslib.as_array(ctypes.cast(slab, ctypes.POINTER(ctypes.c_uint32)), shape=(int(sinfo[1]) // 4,))
+        off = (td[:, 0].astype(np.int64) | (td[:, 1].astype(np.int64) << 32)) // 4
+        res[key + "_bytes"] = td[:, 2]
+        res[key + "_level"] = td[:, 3]
+        res[key + "_first"] = sl[off] & 0xff
+    lib.chb_schedule_destroy(hs)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     np.savez_compressed(out, **res)
     print("wrote", out)
