@@ -77,11 +77,13 @@ int padded_rhs(int k) { return (k + 3) & ~3; }  // row stride of the work vector
 
 int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 RHS columns (+ 1 loader warp)
 
-// Rows of the shared-memory row ring: room for the largest local task plus two full blocks, up to about
-// 92 KB (two CTAs per SM at 128 right-hand sides).
+// Rows of the shared-memory row ring: room for the largest local task plus two full blocks, about 40 KB
+// (four CTAs per SM at 128 single-precision right-hand sides; measured: occupancy beats ring depth).
 int sweep_ring_rows(int elem, int k, int local_rows) {
     const int row_bytes = padded_rhs(k) * elem;
-    return std::max(local_rows + 32, std::min(256, (92 << 10) / row_bytes));
+    int budget_kb = 40;
+    if (const char *v = std::getenv("CHB_RING_KB")) budget_kb = std::max(1, std::atoi(v));
+    return std::max(local_rows + 32, std::min(256, (budget_kb << 10) / row_bytes));
 }
 
 // Dynamic shared memory of one sweep CTA (sweep.cuh: struct Smem).
@@ -268,6 +270,7 @@ GpuSolver::~GpuSolver() {
     dev_free(m_counters);
     dev_free(m_tmp);
     dev_free(m_scratch);
+    dev_free(m_rbuf);
     dev_free(m_stage_b);
     dev_free(m_stage_x);
 }
@@ -331,6 +334,7 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
         a.src = (const Float *) src;
         a.dst = (Float *) dst;
         a.scratch = (Float *) m_scratch;
+        a.rbuf = (Float *) m_rbuf;
         a.trace = (unsigned long long *) s.trace;
     };
     SweepArgs<float> a32;
@@ -358,6 +362,8 @@ void GpuSolver::solve(int k, const void *b, void *x) {
     if (k != m_k) {
         dev_free(m_tmp);
         dev_free(m_scratch);
+        dev_free(m_rbuf);
+        m_rbuf = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) padded_rhs(k));
         m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) padded_rhs(k));
         const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
         m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) padded_rhs(k));

@@ -109,6 +109,7 @@ private:
 
     void *m_counters = nullptr; // int32[8]: [0,1] sweep tickets, [2] analysis ticket, [3] analysis max level
     void *m_tmp = nullptr;      // Float[n*k]
+    void *m_rbuf = nullptr;     // Float[n*round4(k)]: residuals of the inverse super-blocks
     void *m_scratch = nullptr;  // Float[max n_slots * 16 * k]: parked partial tiles
     void *m_stage_b = nullptr, *m_stage_x = nullptr;  // device staging for solve_host
     size_t m_stage_bytes = 0;

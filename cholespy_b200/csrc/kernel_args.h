@@ -40,6 +40,7 @@ struct SweepArgs {
     const Float *src;     // forward: user's b
     Float *dst;           // backward: user's x
     Float *scratch;       // n_slots tiles of 16 x round4(k)
+    Float *rbuf;          // (n, round4(k)) residual vector of the inverse super-blocks
     unsigned long long *trace;  // optional (debug): 8 words per task {start ns, slab ready ns, end ns, cycles spent waiting, last wait ns, blocks done ns, triangle done ns, -}
 };
 

@@ -68,6 +68,7 @@ ScheduleOptions schedule_options_from_env() {
     o.local_rows = std::max(0, std::min(240, geti("CHB_LOCAL_ROWS", o.local_rows)));
     o.local_ext = std::max(0, geti("CHB_LOCAL_EXT", o.local_ext));
     o.local_cost = std::max(1, geti("CHB_LOCAL_COST", o.local_cost));
+    o.inv_panels = std::max(0, std::min(64, geti("CHB_INV_PANELS", o.inv_panels)));
     o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));
     o.chunk_cost = std::max(256, geti("CHB_CHUNK_COST", o.chunk_cost));
     if (const char *v = std::getenv("CHB_RELAX_ALPHA")) o.relax_alpha = std::max(1.0, std::atof(v));
@@ -185,9 +186,12 @@ struct Builder {
     bool local = false;
     int loc_lo = 0, loc_n_int = 0;
     std::vector<int> loc_ext;
+    // inverse super-blocks: A tasks end by storing the residual instead of solving the triangle
+    bool end_store_r = false;
+    std::vector<int> atask_of_panel;
 
     Builder(const HostFactor &L_, const PanelStructure &S_, const ScheduleOptions &o, SweepImage &i)
-        : L(L_), S(S_), opt(o), img(i), w(i.slab, i.page_bytes, i.elem), upper(i.upper), task_of_panel(S_.n_panels, -1) {}
+        : L(L_), S(S_), opt(o), img(i), w(i.slab, i.page_bytes, i.elem), upper(i.upper), task_of_panel(S_.n_panels, -1), atask_of_panel(S_.n_panels, -1) {}
 
     // -- tasks ----------------------------------------------------------------------------------
     int open_task() {
@@ -376,7 +380,35 @@ struct Builder {
         task_of_panel[P] = cur;
     }
 
+    // END_STORE: the tile goes to the residual vector (A task of an inverse super-block) or, as the
+    // solved unknowns, to the work vector (B task)
+    void emit_end_store(int P, bool to_residual) {
+        const int wd = S.width(P), row0 = S.c0[P];
+        const size_t head = upper && !to_residual ? 4 * kPanelWidth : 0;
+        const size_t off = w.record(REC_END_STORE, row0, (uint32_t) wd, to_residual ? 1u : 0u, head);
+        if (head)
+            for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
+        if (to_residual) atask_of_panel[P] = cur;
+        else task_of_panel[P] = cur;
+    }
+
+    // A dense block of an inverse super-block: tile -= V * r[rows of panel p]; value(r, t) = V[target t][source
+    // r-th in sweep order].
+    template <typename ValueFn>
+    void emit_inverse_block(int p, int n_targets, int dep_task, ValueFn value) {
+        const int ns = S.width(p);
+        const uint32_t smask = (1u << ns) - 1, tmask = (1u << n_targets) - 1;
+        const int stride = (n_targets + 3) & ~3;
+        const size_t off = w.record(REC_BLOCK_D4 | REC_SRC_R_FLAG, S.c0[p], smask | tmask << 16, wait_code(dep_task),
+                                    (size_t) img.elem * (size_t) ns * (size_t) stride);
+        for (int r = 0; r < ns; ++r)
+            for (int t = 0; t < n_targets; ++t) w.put_value(off, (size_t) r * stride + t, value(r, t));
+        img.n_blocks += 1;
+        img.n_stored_values += (int64_t) ns * stride;
+    }
+
     void emit_end_final(int P) {
+        if (end_store_r) return emit_end_store(P, true);
         if (!opt.exact_order) return emit_end_dense(P);
         const int wd = S.width(P), row0 = S.c0[P];
         const size_t es = (size_t) img.elem;
@@ -520,7 +552,7 @@ struct Builder {
             sub_count[q] += sub_count[P];
             first[q] = std::min(first[q], first[P]);
         }
-        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 32 : 64);
+        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 16 : 32);
         std::vector<int> root_of(np, -1);  // root of the local task a panel belongs to, or -1
         for (int P = np - 1; P >= 0; --P) {
             if (root_of[P] >= 0) continue;  // already inside a local subtree
@@ -529,6 +561,91 @@ struct Builder {
             if (contiguous && rows <= max_rows && S.m[P] <= opt.local_ext && rows + S.m[P] <= 255 && sub_cost[P] <= opt.local_cost)
                 for (int q = first[P]; q <= P; ++q) root_of[q] = P;
         }
+        // Inverse super-blocks: runs of <= inv_panels consecutive panels of one supernode (outside local tasks)
+        std::vector<int> sb_lo(np, -1), sb_hi(np, -1);
+        if (!opt.exact_order && opt.inv_panels >= 2) {
+            auto continues = [&](int P) {  // panel P continues the supernode of panel P - 1
+                if (P <= 0 || root_of[P] >= 0 || root_of[P - 1] >= 0 || S.parent[P - 1] != P) return false;
+                const int wd = S.width(P);
+                if (S.m[P - 1] != wd + S.m[P]) return false;
+                const int *R = &S.rows[(size_t) S.rlo[P - 1]];
+                return R[0] == S.c0[P] && R[wd - 1] == S.c0[P + 1] - 1;
+            };
+            int P = 0;
+            while (P < np) {
+                int Q = P;
+                while (Q + 1 < np && Q + 1 - P < opt.inv_panels && continues(Q + 1)) ++Q;
+                if (Q > P)
+                    for (int q = P; q <= Q; ++q) sb_lo[q] = P, sb_hi[q] = Q;
+                P = Q + 1;
+            }
+        }
+        std::vector<double> tinv;  // inverse of the current super-block's dense triangle, row-major nJ x nJ
+        int tinv_lo = -1;
+        auto prepare_inverse = [&](int lo, int hi) {
+            if (tinv_lo == lo) return;
+            tinv_lo = lo;
+            const int c_lo = S.c0[lo], nJ = S.c0[hi + 1] - c_lo;
+            std::vector<double> T((size_t) nJ * nJ, 0.0);
+            int64_t present = 0;
+            for (int j = 0; j < nJ; ++j)
+                for (int e = L.colptr[c_lo + j]; e < L.colptr[c_lo + j + 1] && L.rowidx[e] < c_lo + nJ; ++e) {
+                    T[(size_t) (L.rowidx[e] - c_lo) * nJ + j] = L.vals[(size_t) e];
+                    present += 1;
+                }
+            img.n_values += present;  // the super-block's own entries are consumed through the inverse
+            tinv.assign((size_t) nJ * nJ, 0.0);
+            for (int c = 0; c < nJ; ++c) {  // column c of the inverse: T x = e_c by forward substitution
+                for (int i = c; i < nJ; ++i) {
+                    double acc = i == c ? 1.0 : 0.0;
+                    for (int q = c; q < i; ++q) acc -= T[(size_t) i * nJ + q] * tinv[(size_t) q * nJ + c];
+                    tinv[(size_t) i * nJ + c] = acc / T[(size_t) i * nJ + i];
+                }
+            }
+        };
+        // panel P of the inverse super-block [lo, hi]: task(s) A (residual) then task B (inverse apply)
+        auto emit_inverse_panel = [&](int P) {
+            const int lo = sb_lo[P], hi = sb_hi[P];
+            prepare_inverse(lo, hi);
+            const int c_lo = S.c0[lo], nJ = S.c0[hi + 1] - c_lo;
+            blocks_of(P, blocks);
+            // blocks whose partner panel lies inside the super-block are replaced by the inverse
+            std::vector<int64_t> outside;
+            int64_t a_cost = 0;
+            for (int64_t b : blocks) {
+                const int partner = upper ? S.b_tgt[b] : S.b_src[b];
+                if (partner >= lo && partner <= hi) continue;
+                outside.push_back(b);
+                a_cost += block_cost(b);
+            }
+            end_store_r = true;
+            if (a_cost > opt.split_cost) {
+                emit_split_panel(P, outside);
+            } else {
+                open_task();
+                emit_panel(P, outside);
+                close_task();
+            }
+            end_store_r = false;
+            open_task();
+            emit_begin_zero(P);
+            const int wP = S.width(P), oP = S.c0[P] - c_lo;
+            if (!upper) {
+                for (int p = lo; p <= P; ++p) {
+                    const int op = S.c0[p] - c_lo;
+                    emit_inverse_block(p, wP, atask_of_panel[p], [&](int r, int t) { return -tinv[(size_t) (oP + t) * nJ + (op + r)]; });
+                }
+            } else {
+                for (int p = hi; p >= P; --p) {
+                    const int op = S.c0[p] - c_lo, wp = S.width(p);
+                    // sources = rows of p visited descending; unknowns = columns of P
+                    emit_inverse_block(p, wP, atask_of_panel[p], [&](int r, int t) { return -tinv[(size_t) (op + wp - 1 - r) * nJ + (oP + t)]; });
+                }
+            }
+            emit_end_store(P, false);
+            close_task();
+        };
+
         int i = 0;
         while (i < np) {
             // [lo, hi] = the next run of panels forming one task, in this sweep's processing order
@@ -544,6 +661,10 @@ struct Builder {
             i += hi - lo + 1;
             if (root_of[hi] >= 0) {
                 emit_local_task(lo, hi, blocks);
+                continue;
+            }
+            if (sb_lo[lo] >= 0) {
+                emit_inverse_panel(lo);
                 continue;
             }
             blocks_of(lo, blocks);

@@ -28,6 +28,14 @@
 //   slab    the byte stream of one task: 16-byte-aligned records (below), streamed through shared
 //           memory in pages by 1-D TMA bulk copies; no record straddles a page boundary.
 //
+// Inverse super-blocks (fast mode).  The panels of one wide supernode form a dependency CHAIN: panel t
+// needs panel t - 1, one global hop per 16 columns, and the elimination tree's top separators make
+// that chain hundreds of hops long.  For every run J of <= inv_panels consecutive panels of one
+// supernode the dense triangle T = L[J, J] is therefore inverted on the host (double precision) and
+// each panel t of J gets two tasks: A(t) accumulates r[t] = rhs[t] - (blocks from outside J) into the
+// residual vector r, B(t) computes x[t] = sum_{p in J} Tinv[t, p] r[p] from the residuals of J.  All
+// A tasks of J run in parallel, then all B tasks: two hops per run instead of one per panel.
+//
 // Forward sweep (L y = P b): task of panel t PULLS from the panels p < t it has blocks with:
 //   tile[t] = b[perm[rows(t)]] - sum_p L[rows(t), cols(p)] y[cols(p)], then the in-panel triangle.
 // Backward sweep (L' x = y): task of panel p PULLS from the panels t > p owning its rows R:
@@ -69,6 +77,9 @@ enum RecordType : uint32_t {
                          // local[n_int + e] = tmp[ext_row[e]] after every wait code has published
     REC_LOCAL_STORE = 12,// a = row_lo, b = n_int.  payload backward: perm[n_int].  tmp[row_lo + i] = local[i]
                          // (backward: also x[perm[i]] = local[i]); the task's last record
+    REC_END_STORE = 13,  // a = row0, b = w, c = destination: 0 = the work vector (payload backward: perm[16]; publishes the
+                         // panel), 1 = the residual vector r of an inverse super-block.  No triangle.
+    REC_SRC_R_FLAG = 0x80, // on a BLOCK record: the source rows are rows of the residual vector r, not of the work vector
     // Inside a local task the BEGIN_RHS / BLOCK_* / END_FINAL / END_DENSE records carry REC_LOCAL_FLAG:
     //   BEGIN_RHS: a = local index of the panel's first row, no payload (tile = local rows)
     //   BLOCK_*:   a unused, c = 0; payload starts with 16 bytes = local index of each source row in
@@ -78,13 +89,15 @@ enum RecordType : uint32_t {
 };
 
 struct ScheduleOptions {
-    int local_rows = 0;       // a complete subtree becomes one LOCAL task up to this many rows (0: 64 f32 / 32 f64)
-    int local_ext = 32;       // ... this many external rows below its root panel (backward sweep)
+    int local_rows = 0;       // a complete subtree becomes one LOCAL task up to this many rows (0: 32 f32 / 16 f64)
+    int local_ext = 16;       // ... this many external rows below its root panel (backward sweep)
     int local_cost = 16384;   // ... and this many stored values
     int split_cost = 8192;    // a panel with more values than this is split into chunk tasks
     int chunk_cost = 4096;    // values per chunk task
     double relax_alpha = 1.5; // relaxed panels: stored values <= alpha * non-zeros + beta (1.0 / 0: no fill)
     double relax_beta = 32.0;
+    int inv_panels = 8;       // consecutive panels of one supernode whose diagonal block is applied as an explicit
+                              // inverse (fast mode only; < 2: off).  See "inverse super-blocks" below.
     bool exact_order = false; // true: chunks are CHAINED (reference summation order kept bit for bit)
                               // false: chunks run in parallel and are summed in a fixed order
 };

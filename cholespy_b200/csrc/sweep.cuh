@@ -53,7 +53,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 enum : uint32_t { REC_NOP = 0, REC_BEGIN_RHS, REC_BEGIN_ZERO, REC_BEGIN_SLOT, REC_ADD_SLOT, REC_BLOCK_D4, REC_BLOCK_D1,
                   REC_BLOCK_TM, REC_END_FINAL, REC_END_SLOT, REC_END_DENSE, REC_LOCAL_LOAD, REC_LOCAL_STORE,
-                  REC_LOCAL_FLAG = 0x40 };
+                  REC_END_STORE, REC_LOCAL_FLAG = 0x40, REC_SRC_R_FLAG = 0x80 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -267,7 +267,7 @@ __device__ __forceinline__ void run_block(F (&T)[W], uint32_t masks, const unsig
 // Records whose input rows the LOADER stages into the row ring.  Returns the number of rows, 0 if the
 // record needs no rows (those are handled by the compute warps alone).
 __device__ __forceinline__ int staged_rows(const uint4 &h) {
-    const uint32_t type = h.x & 0xff;  // records inside local tasks carry REC_LOCAL_FLAG and never match
+    const uint32_t type = h.x & 0x7f;  // records inside local tasks carry REC_LOCAL_FLAG and never match
     if (type == REC_BLOCK_D4) return __popc(h.z & 0xffff);
     if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) return W;
     if (type == REC_BEGIN_RHS) return (int) h.z;
@@ -405,7 +405,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                 while (qp < pend && n < 32) {
                     const uint4 hq = *reinterpret_cast<const uint4 *>(qp);
                     if (staged_rows(hq) > 0) {
-                        const uint32_t tq = hq.x & 0xff;
+                        const uint32_t tq = hq.x & 0x7f;
                         const bool many = tq == REC_LOCAL_LOAD && hq.w != 0;
                         if (many && n > 0) break;
                         if (lane == n) {
@@ -449,7 +449,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                 for (int i = 0; i < n_go; ++i) {
                     const unsigned char *rec = p + __shfl_sync(kFullMask, my_off, i);
                     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
-                    const uint32_t type = h.x & 0xff;
+                    const uint32_t type = h.x & 0x7f;
                     const int nr = staged_rows(h);
                     // back-pressure: a free barrier pair and nr free rows in the ring
                     while (j_issue - j_rel >= (uint32_t) kRowBars || rows_in_flight + nr > ring_rows) {
@@ -473,8 +473,9 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                             m &= ~(((1u << len) - 1u) << s);
                             n_runs += 1;
                         }
+                        const F *from = (h.x & REC_SRC_R_FLAG) ? a.rbuf : a.tmp;  // residuals of an inverse super-block
                         if (lane < n_runs)
-                            copy_rows(wrap(head + my_rank, ring_rows), a.tmp + (size_t) ((int) h.y + my_start) * kp, my_len, bar);
+                            copy_rows(wrap(head + my_rank, ring_rows), from + (size_t) ((int) h.y + my_start) * kp, my_len, bar);
                     } else if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) {
                         if (lane == 0) copy_rows(head, a.scratch + (size_t) (h.z >> 8) * W * kp, W, bar);
                     } else if (type == REC_BEGIN_RHS) {
@@ -627,6 +628,16 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         }
                     } else {
                         store_tile(perm);
+                    }
+                } else if (type == REC_END_STORE) {
+                    if (h.w == 1) {  // residual of an inverse super-block
+                        if (active) {
+#pragma unroll
+                            for (int i = 0; i < W; ++i)
+                                if (i < w) __stcg(a.rbuf + (size_t) (row0 + i) * kp + col, T[i]);
+                        }
+                    } else {
+                        store_tile(reinterpret_cast<const int *>(pay));
                     }
                 } else if (type == REC_LOCAL_LOAD) {
                     lrows = (int) (h.z & 0xffff) + (int) (h.z >> 16);

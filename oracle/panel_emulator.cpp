@@ -26,7 +26,7 @@ inline double fnma(double a, double b, double c) { return __builtin_fma(-a, b, c
 inline int span16(uint32_t m) { return m ? 32 - __builtin_clz(m) : 0; }
 
 enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT, END_DENSE,
-       LOCAL_LOAD, LOCAL_STORE, LOCAL_FLAG = 0x40 };
+       LOCAL_LOAD, LOCAL_STORE, END_STORE, LOCAL_FLAG = 0x40, SRC_R_FLAG = 0x80 };
 
 // returns 0, or a negative error code
 template <typename F>
@@ -34,6 +34,7 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
         const F *b, F *x, F *scratch) {
     std::vector<uint8_t> done((size_t) n_tasks, 0);
     std::vector<F> acc((size_t) W * k);
+    std::vector<F> rbuf;  // residual vector of the inverse super-blocks (grown on demand)
     std::vector<F> loc;  // rows of the local task being executed: [n_int unknowns | n_ext external rows] x k
     int loc_rows = 0;
     auto waited = [&](uint32_t c) { return c == 0 || done[c - 1]; };
@@ -51,6 +52,7 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                 std::memcpy(h, base + pg + p, 16);
                 const uint32_t type = h[0] & 0x3f, len = (h[0] >> 8) * 16;
                 const bool local = (h[0] & LOCAL_FLAG) != 0;
+                const bool src_r = (h[0] & SRC_R_FLAG) != 0;
                 if (len < 16 || p + len > plen) return -3;  // record straddles a page
                 const uint8_t *pay = base + pg + p + 16;
                 const uint8_t *src_idx = pay;  // local blocks: 16 local source-row indices first
@@ -58,6 +60,7 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                 const F *v = (const F *) pay;
                 // row `s` (sweep order rank r) of a block's source panel
                 auto source_row = [&](int src0, int s, int r) -> const F * {
+                    if (src_r) return (size_t) (src0 + s + 1) * k <= rbuf.size() ? rbuf.data() + (size_t) (src0 + s) * k : nullptr;
                     if (!local) return tmp + (size_t) (src0 + s) * k;
                     if ((int) src_idx[r] >= loc_rows) return nullptr;
                     return loc.data() + (size_t) src_idx[r] * k;
@@ -190,6 +193,21 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                             tmp[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
                             if (upper) x[(size_t) perm[i] * k + c] = acc[(size_t) i * k + c];
                         }
+                } break;
+                case END_STORE: {
+                    if ((int) h[1] != row0 || (int) h[2] != w) return -5;
+                    const int32_t *perm = (const int32_t *) pay;
+                    if (h[3] == 1) {
+                        if (rbuf.size() < (size_t) (row0 + w) * k) rbuf.resize((size_t) (row0 + w) * k, F(0));
+                        for (int i = 0; i < w; ++i)
+                            for (int c = 0; c < k; ++c) rbuf[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
+                    } else {
+                        for (int i = 0; i < w; ++i)
+                            for (int c = 0; c < k; ++c) {
+                                tmp[(size_t) (row0 + i) * k + c] = acc[(size_t) i * k + c];
+                                if (upper) x[(size_t) perm[i] * k + c] = acc[(size_t) i * k + c];
+                            }
+                    }
                 } break;
                 case END_SLOT: {
                     F *s = scratch + (size_t) (h[2] >> 8) * W * k;
