@@ -148,43 +148,73 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path (CHOLMOD solve_cpu)
 # ------------------------------------------------------------------------------------------------
+_REF_SOLVE = None  # set before the worker pool forks: workers inherit the factorised reference solver
+
+
+def _ref_worker(b):
+    _REF_SOLVE(b)
+    return b.shape[1]
+
+
 def run_reference(args, name, p, k, dtype):
+    """The reference's own CPU implementation of the path: CholeskySolver<Float>::solve_cpu (CHOLMOD
+    simplicial solve, reference src/cholesky_solver.cpp:434-463) compiled unmodified into oracle/_ref.
+    That solve is single-threaded by construction, so "all the host threads it can use" = one forked
+    worker per core, each solving its own block of 4 RHS columns (CHOLMOD's internal column blocking)
+    of one step's sample concurrently with the same factor."""
+    import multiprocessing as mp
+    global _REF_SOLVE
     from oracle import oracle
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_k = min(k, args.ref_columns)
     t = time.time()
     if oracle.reference_available():
         kind = "reference"
         ref = oracle.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=True)
         log("reference constructor (CHOLMOD analyze+factorize): %.1f s" % (time.time() - t))
-        solve = lambda b: ref.solve_cpu(b)  # noqa: E731
+        _REF_SOLVE = lambda b: ref.solve_cpu(b)  # noqa: E731
     else:
         kind = "port"
         perm, cp, ri, v = get_factor(name, p)
-        solve = lambda b: oracle.solve(cp, ri, v, perm, b)  # noqa: E731
+        _REF_SOLVE = lambda b: oracle.solve(cp, ri, v, perm, b)  # noqa: E731
+    cores = max(1, min(os.cpu_count() or 1, args.ref_procs, (k + 3) // 4))
+    sample_k = min(k, 4 * cores)
     rng = np.random.default_rng(45)
     b = rng.random((p["n"], sample_k)).astype(dtype)
+    parts = [np.ascontiguousarray(b[:, c:c + 4]) for c in range(0, sample_k, 4)]
+    pool = None
+    if cores > 1:
+        try:
+            pool = mp.get_context("fork").Pool(cores)
+        except (OSError, ValueError) as e:
+            log("fork pool unavailable (%s): single process" % e)
+            cores = 1
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        solve(b)
+        if pool:
+            pool.map(_ref_worker, parts, chunksize=1)
+        else:
+            for part in parts:
+                _REF_SOLVE(part)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
         if sum(times) > args.ref_budget_s and len(times) >= 1:
             break
+    if pool:
+        pool.close()
     ms = 1e3 * float(np.mean(times))
     value = sample_k / (ms * 1e-3)
-    sample = "%d of %d RHS columns per step, %d timed steps, 1 thread (CHOLMOD's simplicial solve is single-threaded)" % (
-        sample_k, k, len(times))
+    sample = "%d of %d RHS columns per step (4 per worker), %d timed steps, %d worker processes sharing one factor (CHOLMOD's simplicial solve is single-threaded)" % (
+        sample_k, k, len(times), cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
         "config": {"workload": workload_description(name, p, k, dtype), "sample_columns": sample_k},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores": os.cpu_count(),
     }
@@ -194,36 +224,16 @@ def run_reference(args, name, p, k, dtype):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-class _DevBuf:
-    """Exposes a raw device allocation to torch through __cuda_array_interface__ (zero copy)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
-def image_tensors(lib, handle, device):
-    import torch
-    out = []
-    for i in range(lib.chb_solver_image_count(handle)):
-        name, ptr, nbytes = ctypes.c_char_p(), ctypes.c_void_p(), ctypes.c_uint64()
-        rc = lib.chb_solver_image_buffer(handle, i, ctypes.byref(name), ctypes.byref(ptr), ctypes.byref(nbytes))
-        assert rc == 0
-        out.append((name.value.decode(), torch.as_tensor(_DevBuf(ptr.value, nbytes.value), device=device)))
-    return out
-
-
 def build_solver(args, name, p, k, dtype, rank, world, device):
     """Rank 0 factorises (host, CHOLMOD) and builds the device image; with N > 1 the image (factor
-    both ways + level schedule + permutation) is replicated to every rank by NCCL broadcast."""
+    both ways + task schedule + permutation) is replicated to every rank by NCCL broadcast."""
     import torch
     import torch.distributed as dist
-    from cholespy_b200 import CholeskySolverD, CholeskySolverF, _capi
+    from cholespy_b200 import CholeskySolverD, CholeskySolverF, _capi, multi_gpu
     lib = _capi.load()
     cls = CholeskySolverF if dtype == np.float32 else CholeskySolverD
     code = _capi.F32 if dtype == np.float32 else _capi.F64
     handle = ctypes.c_void_p()
-    meta = torch.zeros(_capi.IMAGE_SHAPE_WORDS, dtype=torch.int64, device=device)
-    t_build = None
     if rank == 0:
         perm, cp, ri, v = get_factor(name, p)
         t = time.time()
@@ -231,34 +241,19 @@ def build_solver(args, name, p, k, dtype, rank, world, device):
         _capi.check(lib.chb_solver_create_from_factor(ctypes.byref(handle), code, len(perm), len(ri), cp.ctypes.data,
                                                       ri.ctypes.data, v.ctypes.data, perm.ctypes.data, device.index))
         t_build = time.time() - t
-        solver = cls._from_handle(handle, len(perm), device.index)
-        info = solver.info()
-        shape = (ctypes.c_int64 * _capi.IMAGE_SHAPE_WORDS)()
-        _capi.check(lib.chb_solver_image_shape(handle, shape, _capi.IMAGE_SHAPE_WORDS))
-        meta = torch.tensor(list(shape), dtype=torch.int64, device=device)
-        log("device image built in %.1f s: n=%d nnz(L)=%d levels=%d/%d tasks=%d/%d slab=%.1f/%.1f MB" % (
-            t_build, info["n"], info["nnz_l"], info["n_levels_lower"], info["n_levels_upper"], info["fwd_tasks"],
-            info["bwd_tasks"], info["fwd_slab_bytes"] / 1e6, info["bwd_slab_bytes"] / 1e6))
-    if world > 1:
-        dist.broadcast(meta, src=0)
-        words = [int(v) for v in meta.tolist()]
-        n = words[0]
-        if rank != 0:
-            _capi.check(lib.chb_init(device.index))
-            shape = (ctypes.c_int64 * _capi.IMAGE_SHAPE_WORDS)(*words)
-            _capi.check(lib.chb_solver_create_replica(ctypes.byref(handle), code, shape, _capi.IMAGE_SHAPE_WORDS, device.index))
-            solver = cls._from_handle(handle, n, device.index)
-        torch.cuda.synchronize()
-        t = time.time()
-        total = 0
-        for bname, tensor in image_tensors(lib, handle, device):
-            dist.broadcast(tensor, src=0)
-            total += tensor.numel()
-        torch.cuda.synchronize()
-        if rank == 0:
-            log("NCCL broadcast of the device image: %.1f MB in %.1f ms" % (total / 1e6, 1e3 * (time.time() - t)))
-    n, z = int(meta[0]), int(meta[1])
-    return solver, n, z, (int(meta[10]), int(meta[11]))
+        info = cls._from_handle(ctypes.c_void_p(handle.value), len(perm), device.index)
+        d = info.info()
+        info._handle = None  # borrowed view only
+        log("device image built in %.1f s: n=%d nnz(L)=%d levels=%d/%d tasks=%d/%d (depth %d/%d) slab=%.1f/%.1f MB" % (
+            t_build, d["n"], d["nnz_l"], d["n_levels_lower"], d["n_levels_upper"], d["fwd_tasks"], d["bwd_tasks"],
+            d["fwd_task_levels"], d["bwd_task_levels"], d["fwd_slab_bytes"] / 1e6, d["bwd_slab_bytes"] / 1e6))
+    torch.cuda.synchronize()
+    t = time.time()
+    solver, words, total = multi_gpu.replicate_solver(cls, handle, code, device, rank, world, dist)
+    torch.cuda.synchronize()
+    if rank == 0 and world > 1:
+        log("NCCL broadcast of the device image: %.1f MB in %.1f ms" % (total / 1e6, 1e3 * (time.time() - t)))
+    return solver, words[0], words[1], (words[10], words[11])
 
 
 def run_b200(args, name, p, k_total, dtype):
@@ -279,7 +274,8 @@ def run_b200(args, name, p, k_total, dtype):
     solver, n, z, nlev = build_solver(args, name, p, k_total, dtype, rank, world, device)
     s = np.dtype(dtype).itemsize
     # RHS-column shard of this rank (columns are independent; no data-path collective)
-    cols = [k_total // world + (1 if r < k_total % world else 0) for r in range(world)]
+    from cholespy_b200 import multi_gpu
+    cols = [c for _, c in multi_gpu.column_shards(k_total, world)]
     k = cols[rank]
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     gen = torch.Generator(device="cpu").manual_seed(45 + rank)
@@ -358,8 +354,12 @@ def run_b200(args, name, p, k_total, dtype):
         # algorithmic bytes = Bytes(k)/2, per-launch duration = step/2 (this rank's shard).
         abytes = algorithmic_bytes(n, z, k, s)
         achieved = abytes / (dev_ms * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture, if any
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            traffic = json.load(open(tpath)).get("%s/k%d/%s" % (args.workload, k_total, "f32" if dtype == np.float32 else "f64"))
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": abytes,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_step": abytes,
                     "launches_per_step": 2, "roofline_columns_per_s": k / (abytes / (peak * 1e9))}
         cpu_baseline = None
         if not args.no_cpu_baseline:
@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--dtype", default="", choices=["", "f", "d"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-columns", type=int, default=32, help="columns of the bounded CPU-baseline sample")
-    ap.add_argument("--ref-columns", type=int, default=16, help="columns per step of the reference arm's sample")
+    ap.add_argument("--ref-procs", type=int, default=64, help="worker processes of the reference arm (capped at the core count)")
     ap.add_argument("--ref-budget-s", type=float, default=60.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)

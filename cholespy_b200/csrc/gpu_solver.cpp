@@ -20,6 +20,7 @@ constexpr int kSweepStages = 4;      // pages in the CTA's slab ring (sweep.cuh:
 constexpr int kSweepRowBars = 16;    // sweep.cuh: kRowBars
 constexpr int kSweepTaskQueue = 4;   // sweep.cuh: kTaskQueue
 constexpr int kFuncAttrMaxDynamicSharedSize = 8;  // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES
+constexpr int kFuncAttrSharedCarveout = 9;        // CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT (percent)
 
 void *dev_alloc(size_t bytes) {
     void *p = nullptr;
@@ -75,13 +76,14 @@ void csc_to_csr_pattern(int n, const std::vector<int> &colptr, const std::vector
 
 int padded_rhs(int k) { return (k + 3) & ~3; }  // row stride of the work vector (whole 16-byte chunks)
 
-int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 RHS columns (+ 1 loader warp)
+int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 RHS columns (+ 1 loader warp).  Wider lanes
+// (2 or 4 columns per lane, fewer warps) were measured slower on ico8 and ico9 at 64..128 RHS: tasks are latency-bound.
 
-// Rows of the shared-memory row ring: room for the largest local task plus two full blocks, about 40 KB
+// Rows of the shared-memory row ring: room for the largest local task plus two full blocks, about 36 KB
 // (four CTAs per SM at 128 single-precision right-hand sides; measured: occupancy beats ring depth).
 int sweep_ring_rows(int elem, int k, int local_rows) {
     const int row_bytes = padded_rhs(k) * elem;
-    int budget_kb = 40;
+    int budget_kb = 36;
     if (const char *v = std::getenv("CHB_RING_KB")) budget_kb = std::max(1, std::atoi(v));
     return std::max(local_rows + 32, std::min(256, (budget_kb << 10) / row_bytes));
 }
@@ -102,6 +104,7 @@ void ImageShape::to_words(int64_t *w) const {
         w[10 + u] = n_levels[u];
         w[12 + u] = max_local_rows[u];
     }
+    w[14] = exact_order;
 }
 ImageShape ImageShape::from_words(const int64_t *w) {
     ImageShape s;
@@ -111,6 +114,7 @@ ImageShape ImageShape::from_words(const int64_t *w) {
         s.n_levels[u] = w[10 + u];
         s.max_local_rows[u] = w[12 + u];
     }
+    s.exact_order = w[14];
     return s;
 }
 
@@ -205,6 +209,7 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     // Host: lay the factor out as the two sweep images (one thread each) while the device runs the
     // level analysis of both triangles.
     const ScheduleOptions opt = schedule_options_from_env();
+    m_exact = opt.exact_order;
     PanelStructure structure;
     build_panel_structure(L, opt, &structure);
     SweepImage img[2];
@@ -252,6 +257,7 @@ GpuSolver::GpuSolver(int device, int elem_size, const ImageShape &shape)
         m_sweep[u].max_local_rows = (int) shape.max_local_rows[u];
         allocate_sweep(m_sweep[u]);
     }
+    m_exact = shape.exact_order != 0;
     m_lower.n_levels = (int) shape.n_levels[0];
     m_upper.n_levels = (int) shape.n_levels[1];
     sync0();
@@ -285,6 +291,7 @@ ImageShape GpuSolver::shape() const {
         s.n_task_levels[u] = m_sweep[u].n_task_levels;
         s.max_local_rows[u] = m_sweep[u].max_local_rows;
     }
+    s.exact_order = m_exact ? 1 : 0;
     s.n_levels[0] = m_lower.n_levels;
     s.n_levels[1] = m_upper.n_levels;
     return s;
@@ -303,13 +310,14 @@ std::vector<ImageBuffer> GpuSolver::image() const {
 
 void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
     char name[64];
-    snprintf(name, sizeof name, "chb_sweep_%s_%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower");
+    snprintf(name, sizeof name, "chb_sweep_%s_%s%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower", m_exact ? "_exact" : "");
     CUfunction fn = kernel(m_dev, name);
     if (!fn) throw std::runtime_error(driver_error_text());
     const int local_rows = std::max(m_sweep[0].max_local_rows, m_sweep[1].max_local_rows);
     const size_t smem = sweep_smem_bytes(m_elem, k, local_rows);
     const int block = 32 * (sweep_warps(k) + 1);
     cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
+    cuda_check(cuFuncSetAttribute(fn, kFuncAttrSharedCarveout, 100));  // all of the SM's L1/shared array as shared memory
 
     int *counters = (int *) m_counters;
     int *ticket = counters + (m_sweeps & 1), *ticket_next = counters + ((m_sweeps + 1) & 1);

@@ -47,7 +47,8 @@ struct ImageShape {
     int64_t n_tasks[2] = {0, 0}, slab_bytes[2] = {0, 0}, n_slots[2] = {0, 0}, n_task_levels[2] = {0, 0};
     int64_t n_levels[2] = {0, 0};  // reference level counts (lower, upper)
     int64_t max_local_rows[2] = {0, 0};
-    static constexpr int kWords = 14;
+    int64_t exact_order = 0;  // the image was built with ScheduleOptions::exact_order (selects the *_exact kernels)
+    static constexpr int kWords = 15;
     void to_words(int64_t *w) const;
     static ImageShape from_words(const int64_t *w);
 };
@@ -102,6 +103,7 @@ private:
     int m_epoch = 0;
     int m_sweeps = 0;
     int m_last_grid = 0;
+    bool m_exact = false;       // exact-order schedule: packed triangles + IEEE division (the *_exact kernels)
 
     TriangleAnalysis m_lower, m_upper;
     std::vector<int> m_perm_host;

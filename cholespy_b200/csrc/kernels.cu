@@ -59,7 +59,11 @@ extern "C" __global__ void __launch_bounds__(256) chb_analysis(const AnalysisArg
             for (int e = beg + lane; e < end; e += 32) {
                 const int *dep = a.level + a.colidx[e];
                 int d;
-                while ((d = ld_relaxed(dep)) < 0) {}
+                unsigned backoff = 32;
+                while ((d = ld_relaxed(dep)) < 0) {  // back off: thousands of polling warps would saturate L2
+                    __nanosleep(backoff);
+                    if (backoff < 1024) backoff *= 2;
+                }
                 lvl = max(lvl, d + 1);
             }
 #pragma unroll

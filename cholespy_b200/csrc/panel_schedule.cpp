@@ -66,7 +66,7 @@ ScheduleOptions schedule_options_from_env() {
     };
     o.exact_order = geti("CHB_EXACT_ORDER", 0) != 0;
     o.local_rows = std::max(0, std::min(240, geti("CHB_LOCAL_ROWS", o.local_rows)));
-    o.local_ext = std::max(0, geti("CHB_LOCAL_EXT", o.local_ext));
+    o.local_ext = std::max(0, std::min(31, geti("CHB_LOCAL_EXT", o.local_ext)));  // one loader lane per external row
     o.local_cost = std::max(1, geti("CHB_LOCAL_COST", o.local_cost));
     o.inv_panels = std::max(0, std::min(64, geti("CHB_INV_PANELS", o.inv_panels)));
     o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));

@@ -461,40 +461,45 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     uint64_t *bar = sm.rfull + j_issue % kRowBars;
                     if (lane == 0) sm.rows_of[j_issue % kRowBars] = nr;
                     uint32_t tx = (uint32_t) nr * row_bytes;
+                    // what this lane copies: n_copy consecutive rows from `from` to ring row `slot` (one TMA copy, two
+                    // if it wraps); rows of the user's b (scattered through P) are handled below
+                    const F *from = nullptr;
+                    int slot = head, n_copy = 0;
+                    const int *rhs_perm = nullptr;
+                    int rhs_n = 0;
                     if (type == REC_BLOCK_D4) {
                         // runs of consecutive source rows, ascending: lane r copies run r
                         uint32_t m = h.z & 0xffff;
-                        int rank = 0, n_runs = 0, my_start = 0, my_len = 0, my_rank = 0;
+                        int rank = 0, n_runs = 0;
+                        const F *rows = ((h.x & REC_SRC_R_FLAG) ? a.rbuf : a.tmp) + (size_t) (int) h.y * kp;
                         while (m) {
-                            const int s = __ffs(m) - 1;
-                            const int len = __ffs(~(m >> s)) - 1;
-                            if (lane == n_runs) my_start = s, my_len = len, my_rank = rank;
+                            const int s0 = __ffs(m) - 1;
+                            const int len = __ffs(~(m >> s0)) - 1;
+                            if (lane == n_runs) from = rows + (size_t) s0 * kp, n_copy = len, slot = wrap(head + rank, ring_rows);
                             rank += len;
-                            m &= ~(((1u << len) - 1u) << s);
+                            m &= ~(((1u << len) - 1u) << s0);
                             n_runs += 1;
                         }
-                        const F *from = (h.x & REC_SRC_R_FLAG) ? a.rbuf : a.tmp;  // residuals of an inverse super-block
-                        if (lane < n_runs)
-                            copy_rows(wrap(head + my_rank, ring_rows), from + (size_t) ((int) h.y + my_start) * kp, my_len, bar);
                     } else if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) {
-                        if (lane == 0) copy_rows(head, a.scratch + (size_t) (h.z >> 8) * W * kp, W, bar);
+                        if (lane == 0) from = a.scratch + (size_t) (h.z >> 8) * W * kp, n_copy = W;
                     } else if (type == REC_BEGIN_RHS) {
                         if (UPPER) {
-                            if (lane == 0) copy_rows(head, a.tmp + (size_t) (int) h.y * kp, nr, bar);
+                            if (lane == 0) from = a.tmp + (size_t) (int) h.y * kp, n_copy = nr;
                         } else {
-                            tx = copy_rhs_rows(reinterpret_cast<const int *>(rec + 16), nr);
+                            rhs_perm = reinterpret_cast<const int *>(rec + 16), rhs_n = nr;
                         }
                     } else {  // REC_LOCAL_LOAD
                         const int n_int = (int) (h.z & 0xffff), n_ext = (int) (h.z >> 16);
                         const int *list = reinterpret_cast<const int *>(rec + 16);
-                        if (UPPER) {
-                            if (lane == 0) copy_rows(head, a.tmp + (size_t) (int) h.y * kp, n_int, bar);
-                            for (int e = lane; e < n_ext; e += 32)
-                                copy_rows(wrap(head + n_int + e, ring_rows), a.tmp + (size_t) list[e] * kp, 1, bar);
+                        if (UPPER) {  // lane 31: the task's own rows (one run); lanes < n_ext (<= 31): one external row each
+                            if (lane == 31) from = a.tmp + (size_t) (int) h.y * kp, n_copy = n_int;
+                            else if (lane < n_ext) from = a.tmp + (size_t) list[lane] * kp, n_copy = 1, slot = wrap(head + n_int + lane, ring_rows);
                         } else {
-                            tx = copy_rhs_rows(list, n_int);
+                            rhs_perm = list, rhs_n = n_int;
                         }
                     }
+                    if (n_copy > 0) copy_rows(slot, from, n_copy, bar);
+                    if (rhs_n > 0) tx = copy_rhs_rows(rhs_perm, rhs_n);
                     __syncwarp();  // manual copies (unaligned right-hand side) are complete before the arrival
                     if (lane == 0) mbar_expect_tx(bar, tx);
                     j_issue += 1;
@@ -512,7 +517,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
 }
 
 // ---- the compute warps -----------------------------------------------------------------------------
-template <typename F, bool UPPER>
+template <typename F, bool UPPER, bool EXACT>
 __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F> &sm, int warp, int lane, int n_compute) {
     const int k = a.k, kp = (k + 3) & ~3;
     const int ring_rows = a.ring_rows;
@@ -556,18 +561,9 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
             head = wrap(head + nr, ring_rows);
         };
         auto ring_at = [&](int base, int i) -> F & { return ring[(size_t) wrap(base + i, ring_rows) * kp]; };
-        // tile -> tmp rows (and, backward, -> x through P')
-        auto store_tile = [&](const int *perm) {
-#pragma unroll
-            for (int i = 0; i < W; ++i) {
-                if (i < w && active) {
-                    __stcg(a.tmp + (size_t) (row0 + i) * kp + col, T[i]);
-                    if (UPPER) a.dst[(size_t) perm[i] * k + col] = T[i];
-                }
-            }
-        };
         // reference-order substitution: packed triangle, IEEE division (exact_order schedules)
         auto tri_exact = [&](const F *tv) {
+            if (!EXACT) return;
 #pragma unroll 1
             for (int step = 0; step < w; ++step) {
                 const int s = UPPER ? w - 1 - step : step;
@@ -616,28 +612,31 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(base, i) : F(0);
                         release_rows(w);
                     }
-                } else if (type == REC_END_DENSE || type == REC_END_FINAL) {
+                } else if (type == REC_END_DENSE || type == REC_END_FINAL || type == REC_END_STORE) {
+                    // (triangle,) then the tile goes to its local rows, to the residual vector, or to the work vector
+                    // (and, backward, through P' to x): one copy of the store code for all of them
                     const int *perm = reinterpret_cast<const int *>(pay);
-                    const F *m = reinterpret_cast<const F *>(pay + (UPPER && !local ? 4 * W : 0));
-                    if (type == REC_END_DENSE) tri_fast(m); else tri_exact(m);
+                    const bool to_residual = type == REC_END_STORE && h.w == 1;
+                    if (type != REC_END_STORE) {
+                        const F *m = reinterpret_cast<const F *>(pay + (UPPER && !local ? 4 * W : 0));
+                        if (EXACT) tri_exact(m); else tri_fast(m);
+                    }
                     if (local) {
                         if (active) {
 #pragma unroll
                             for (int i = 0; i < W; ++i)
                                 if (i < w) ring_at(lbase, row0 + i) = T[i];
                         }
-                    } else {
-                        store_tile(perm);
-                    }
-                } else if (type == REC_END_STORE) {
-                    if (h.w == 1) {  // residual of an inverse super-block
-                        if (active) {
+                    } else if (active) {
+                        F *out = (to_residual ? a.rbuf : a.tmp) + (size_t) row0 * kp + col;
+                        const bool scatter = UPPER && !to_residual;
 #pragma unroll
-                            for (int i = 0; i < W; ++i)
-                                if (i < w) __stcg(a.rbuf + (size_t) (row0 + i) * kp + col, T[i]);
+                        for (int i = 0; i < W; ++i) {
+                            if (i < w) {
+                                __stcg(out + (size_t) i * kp, T[i]);
+                                if (scatter) a.dst[(size_t) perm[i] * k + col] = T[i];
+                            }
                         }
-                    } else {
-                        store_tile(reinterpret_cast<const int *>(pay));
                     }
                 } else if (type == REC_LOCAL_LOAD) {
                     lrows = (int) (h.z & 0xffff) + (int) (h.z >> 16);
@@ -697,7 +696,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
     }
 }
 
-template <typename F, bool UPPER>
+template <typename F, bool UPPER, bool EXACT>
 __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -727,17 +726,23 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
     }
     __syncthreads();
     if (warp == n_compute) loader_warp<F, UPPER>(a, sm, lane);
-    else compute_warp<F, UPPER>(a, sm, warp, lane, n_compute);
+    else compute_warp<F, UPPER, EXACT>(a, sm, warp, lane, n_compute);
 }
 
 }  // namespace sweep
 
-#define CHB_SWEEP(NAME, T, UP)                                                                 \
-    extern "C" __global__ void __launch_bounds__(160, 2) NAME(const chb::SweepArgs<T> a) {          \
-        sweep::sweep_worker<T, UP>(a);                                                         \
+// _exact: kernels for CHB_EXACT_ORDER schedules (packed triangles, IEEE division); the fast kernels do not
+// carry that code (instruction footprint).
+#define CHB_SWEEP(NAME, T, UP, EX)                                                             \
+    extern "C" __global__ void __launch_bounds__(160, 2) NAME(const chb::SweepArgs<T> a) {       \
+        sweep::sweep_worker<T, UP, EX>(a);                                                     \
     }
 
-CHB_SWEEP(chb_sweep_f32_lower, float, false)
-CHB_SWEEP(chb_sweep_f32_upper, float, true)
-CHB_SWEEP(chb_sweep_f64_lower, double, false)
-CHB_SWEEP(chb_sweep_f64_upper, double, true)
+CHB_SWEEP(chb_sweep_f32_lower, float, false, false)
+CHB_SWEEP(chb_sweep_f32_upper, float, true, false)
+CHB_SWEEP(chb_sweep_f64_lower, double, false, false)
+CHB_SWEEP(chb_sweep_f64_upper, double, true, false)
+CHB_SWEEP(chb_sweep_f32_lower_exact, float, false, true)
+CHB_SWEEP(chb_sweep_f32_upper_exact, float, true, true)
+CHB_SWEEP(chb_sweep_f64_lower_exact, double, false, true)
+CHB_SWEEP(chb_sweep_f64_upper_exact, double, true, true)
