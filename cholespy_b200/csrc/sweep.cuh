@@ -217,25 +217,23 @@ struct QueuedTask {
 //   LOCAL:  the rows of the whole local task; idx (16 bytes in front of the values) = local index per source.
 // A plain loop on purpose (small instruction footprint); two sources per iteration hide the LDS latency.
 template <typename F, bool LOCAL, bool UPPER>
-__device__ __forceinline__ void run_block(F (&T)[W], uint32_t masks, const unsigned char *pay, const F *ring, int kp, int base,
-                                          int ring_rows) {
+__device__ __forceinline__ void run_block(F (&T)[W], uint32_t masks, const unsigned char *pay, const F *ring, int kp, int base) {
     const uint32_t tmask = masks >> 16;
     const int ns = __popc(masks & 0xffff);
     const bool g0 = (tmask & 0x000f) != 0, g1 = (tmask & 0x00f0) != 0, g2 = (tmask & 0x0f00) != 0, g3 = (tmask & 0xf000) != 0;
     const int stride = 4 * ((int) g0 + (int) g1 + (int) g2 + (int) g3);
     const F *val = reinterpret_cast<const F *>(pay + (LOCAL ? 16 : 0));
-    int pos = UPPER ? wrap(base + ns - 1, ring_rows) : base;
+    // a record's rows are contiguous in the ring (the loader never lets one wrap around)
+    const F *src = ring + (size_t) (UPPER && !LOCAL ? base + ns - 1 : base) * kp;
 #pragma unroll 2
     for (int r = 0; r < ns; ++r) {
-        int row;
+        F x;
         if (LOCAL) {
-            row = wrap(base + (int) pay[r], ring_rows);
+            x = src[(size_t) pay[r] * kp];
         } else {
-            row = pos;
-            if (UPPER) pos = pos == 0 ? ring_rows - 1 : pos - 1;
-            else pos = pos + 1 == ring_rows ? 0 : pos + 1;
+            x = *src;
+            src = UPPER ? src - kp : src + kp;
         }
-        const F x = ring[(size_t) row * kp];
         const F *v = val;
         if (g0) {
             const Vec4<F> vv = Vec4<F>::load(v);
@@ -329,15 +327,13 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
 
     // n consecutive rows (row_bytes each, contiguous in global memory) -> ring rows slot, slot + 1, ...
     auto copy_rows = [&](int slot, const F *src, int n, uint64_t *bar) {
-        const int first = min(n, ring_rows - slot);
-        tma_load_1d(sm.ring + (size_t) slot * kp, src, (uint32_t) first * row_bytes, bar);
-        if (n > first) tma_load_1d(sm.ring, src + (size_t) first * kp, (uint32_t) (n - first) * row_bytes, bar);
+        tma_load_1d(sm.ring + (size_t) slot * kp, src, (uint32_t) n * row_bytes, bar);
     };
     // rows b[perm[i]], i < n -> ring rows head + i (forward sweep only); returns the TMA bytes to expect
     auto copy_rhs_rows = [&](const int *perm, int n) -> uint32_t {
         if (src_tma) {
             for (int i = lane; i < n; i += 32)
-                tma_load_1d(sm.ring + (size_t) wrap(head + i, ring_rows) * kp, a.src + (size_t) perm[i] * k, src_row_bytes,
+                tma_load_1d(sm.ring + (size_t) (head + i) * kp, a.src + (size_t) perm[i] * k, src_row_bytes,
                             sm.rfull + j_issue % kRowBars);
             return (uint32_t) n * src_row_bytes;
         }
@@ -345,7 +341,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
 #pragma unroll 1
         for (int e = lane; e < total; e += 32) {
             const int i = e / k, c = e - i * k;
-            sm.ring[(size_t) wrap(head + i, ring_rows) * kp + c] = __ldg(a.src + (size_t) perm[i] * k + c);
+            sm.ring[(size_t) (head + i) * kp + c] = __ldg(a.src + (size_t) perm[i] * k + c);
         }
         return 0u;
     };
@@ -451,15 +447,18 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
                     const uint32_t type = h.x & 0x7f;
                     const int nr = staged_rows(h);
-                    // back-pressure: a free barrier pair and nr free rows in the ring
-                    while (j_issue - j_rel >= (uint32_t) kRowBars || rows_in_flight + nr > ring_rows) {
+                    // a record's rows never wrap around the ring: skip the tail if it is too short (the skipped rows
+                    // are accounted to this record).  Back-pressure: a free barrier pair and enough free rows.
+                    int skipped = 0;
+                    if (head + nr > ring_rows) skipped = ring_rows - head, head = 0;
+                    while (j_issue - j_rel >= (uint32_t) kRowBars || rows_in_flight + nr + skipped > ring_rows) {
                         mbar_wait(sm.rempty + j_rel % kRowBars, (j_rel / kRowBars) & 1);
                         rows_in_flight -= sm.rows_of[j_rel % kRowBars];
                         j_rel += 1;
                     }
                     __syncwarp();
                     uint64_t *bar = sm.rfull + j_issue % kRowBars;
-                    if (lane == 0) sm.rows_of[j_issue % kRowBars] = nr;
+                    if (lane == 0) sm.rows_of[j_issue % kRowBars] = nr + skipped;
                     uint32_t tx = (uint32_t) nr * row_bytes;
                     // what this lane copies: n_copy consecutive rows from `from` to ring row `slot` (one TMA copy, two
                     // if it wraps); rows of the user's b (scattered through P) are handled below
@@ -475,7 +474,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                         while (m) {
                             const int s0 = __ffs(m) - 1;
                             const int len = __ffs(~(m >> s0)) - 1;
-                            if (lane == n_runs) from = rows + (size_t) s0 * kp, n_copy = len, slot = wrap(head + rank, ring_rows);
+                            if (lane == n_runs) from = rows + (size_t) s0 * kp, n_copy = len, slot = head + rank;
                             rank += len;
                             m &= ~(((1u << len) - 1u) << s0);
                             n_runs += 1;
@@ -493,7 +492,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                         const int *list = reinterpret_cast<const int *>(rec + 16);
                         if (UPPER) {  // lane 31: the task's own rows (one run); lanes < n_ext (<= 31): one external row each
                             if (lane == 31) from = a.tmp + (size_t) (int) h.y * kp, n_copy = n_int;
-                            else if (lane < n_ext) from = a.tmp + (size_t) list[lane] * kp, n_copy = 1, slot = wrap(head + n_int + lane, ring_rows);
+                            else if (lane < n_ext) from = a.tmp + (size_t) list[lane] * kp, n_copy = 1, slot = head + n_int + lane;
                         } else {
                             rhs_perm = list, rhs_n = n_int;
                         }
@@ -503,8 +502,8 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     __syncwarp();  // manual copies (unaligned right-hand side) are complete before the arrival
                     if (lane == 0) mbar_expect_tx(bar, tx);
                     j_issue += 1;
-                    rows_in_flight += nr;
-                    head = wrap(head + nr, ring_rows);
+                    rows_in_flight += nr + skipped;
+                    head += nr;
                     last = rec + (h.x >> 8) * 16;
                 }
                 p = last;
@@ -548,19 +547,20 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
         int row0 = 0, w = 0;        // the panel whose tile is in registers (row0: global row, or local index)
         int lbase = 0, lrows = 0;   // ring rows of the local task being solved
         // waits for the loader to have staged the next record's rows; returns their ring position
-        auto acquire_rows = [&]() {
+        auto acquire_rows = [&](int nr) {
             const long long c0 = a.trace ? clock64() : 0;
             mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1);
             if (a.trace) wait_cycles += clock64() - c0;
+            if (head + nr > ring_rows) head = 0;  // same rule as the loader: a record's rows never wrap
             return head;
         };
         auto release_rows = [&](int nr) {
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.rempty + j % kRowBars);
             j += 1;
-            head = wrap(head + nr, ring_rows);
+            head += nr;
         };
-        auto ring_at = [&](int base, int i) -> F & { return ring[(size_t) wrap(base + i, ring_rows) * kp]; };
+        auto ring_at = [&](int base, int i) -> F & { return ring[(size_t) (base + i) * kp]; };
         // reference-order substitution: packed triangle, IEEE division (exact_order schedules)
         auto tri_exact = [&](const F *tv) {
             if (!EXACT) return;
@@ -594,10 +594,10 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                 p += (h.x >> 8) * 16;
                 if (type == REC_BLOCK_D4) {
                     if (local) {
-                        run_block<F, true, UPPER>(T, h.z, pay, ring, kp, lbase, ring_rows);
+                        run_block<F, true, UPPER>(T, h.z, pay, ring, kp, lbase);
                     } else {
-                        const int base = acquire_rows();
-                        run_block<F, false, UPPER>(T, h.z, pay, ring, kp, base, ring_rows);
+                        const int base = acquire_rows(__popc(h.z & 0xffff));
+                        run_block<F, false, UPPER>(T, h.z, pay, ring, kp, base);
                         release_rows(__popc(h.z & 0xffff));
                     }
                 } else if (type == REC_BEGIN_RHS) {
@@ -607,7 +607,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
 #pragma unroll
                         for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(lbase, row0 + i) : F(0);
                     } else {
-                        const int base = acquire_rows();
+                        const int base = acquire_rows(w);
 #pragma unroll
                         for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(base, i) : F(0);
                         release_rows(w);
@@ -640,7 +640,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                     }
                 } else if (type == REC_LOCAL_LOAD) {
                     lrows = (int) (h.z & 0xffff) + (int) (h.z >> 16);
-                    lbase = acquire_rows();   // held until LOCAL_STORE
+                    lbase = acquire_rows(lrows);   // held until LOCAL_STORE
                 } else if (type == REC_LOCAL_STORE) {
                     const int lo = (int) h.y, n_int = (int) h.z;
                     const int *perm = reinterpret_cast<const int *>(pay);
@@ -662,7 +662,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         row0 = (int) h.y;
                         w = (int) (h.z & 0xff);
                     }
-                    const int base = acquire_rows();
+                    const int base = acquire_rows(W);
 #pragma unroll
                     for (int i = 0; i < W; ++i) {
                         const F val = ring_at(base, i);
