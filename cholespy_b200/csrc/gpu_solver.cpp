@@ -18,7 +18,7 @@ namespace {
 constexpr int kAnalysisBlock = 256;  // threads per CTA of the analysis kernel
 constexpr int kSweepStages = 4;      // pages in the CTA's slab ring (sweep.cuh: kStages)
 constexpr int kSweepRowBars = 16;    // sweep.cuh: kRowBars
-constexpr int kSweepTaskQueue = 4;   // sweep.cuh: kTaskQueue
+constexpr int kSweepTaskQueue = 8;   // sweep.cuh: kTaskQueue
 constexpr int kFuncAttrMaxDynamicSharedSize = 8;  // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES
 constexpr int kFuncAttrSharedCarveout = 9;        // CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT (percent)
 
@@ -151,9 +151,22 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
     allocate_sweep(d);
     // device task table in ticket order; the `level` word carries the task id (its flag index)
     std::vector<TaskDesc> by_ticket(img.tasks.size());
-    for (size_t t = 0; t < img.order.size(); ++t) {
-        by_ticket[t] = img.tasks[(size_t) img.order[t]];
+    // ... and bits 28-30 of `bytes` say how many tickets a loader may draw together at this position (sweep.cuh):
+    // 8 while at least kWideLevel tasks of the same dependency level are still to be handed out, else 1
+    size_t kWideLevel = 16384;
+    if (const char *v = std::getenv("CHB_WIDE_LEVEL")) kWideLevel = (size_t) std::max(1, std::atoi(v));
+    const size_t nt = img.order.size();
+    size_t level_end = 0;
+    for (size_t t = 0; t < nt; ++t) {
+        const TaskDesc &src = img.tasks[(size_t) img.order[t]];
+        if (t >= level_end) {
+            level_end = t + 1;
+            while (level_end < nt && img.tasks[(size_t) img.order[level_end]].level == src.level) ++level_end;
+        }
+        if (src.bytes >= (1u << 28)) throw std::logic_error("sweep image: task slab too large");
+        by_ticket[t] = src;
         by_ticket[t].level = (uint32_t) img.order[t];
+        by_ticket[t].bytes |= (level_end - t >= kWideLevel ? 7u : 0u) << 28;
     }
     h2d(d.slab, img.slab.data(), img.slab.size());
     h2d(d.tasks, by_ticket.data(), sizeof(TaskDesc) * by_ticket.size());

@@ -92,8 +92,8 @@ struct ScheduleOptions {
     int local_rows = 0;       // a complete subtree becomes one LOCAL task up to this many rows (0: 32 f32 / 16 f64)
     int local_ext = 16;       // ... this many external rows below its root panel (backward sweep)
     int local_cost = 16384;   // ... and this many stored values
-    int split_cost = 8192;    // a panel with more values than this is split into chunk tasks
-    int chunk_cost = 4096;    // values per chunk task
+    int split_cost = 4096;    // a panel with more values than this is split into chunk tasks
+    int chunk_cost = 2048;    // values per chunk task
     double relax_alpha = 1.5; // relaxed panels: stored values <= alpha * non-zeros + beta (1.0 / 0: no fill)
     double relax_beta = 32.0;
     int inv_panels = 32;      // consecutive panels of one supernode whose diagonal block is applied as an explicit

@@ -48,7 +48,8 @@ constexpr int W = 16;            // panel width == tile rows
 constexpr int kStages = 4;       // pages in the CTA's slab ring
 constexpr int kPage = 4096;      // bytes per page (panel_schedule.h: page_bytes_for)
 constexpr int kRowBars = 16;     // staged records in flight (full/empty mbarrier pairs of the row ring)
-constexpr int kTaskQueue = 4;    // task descriptors the loader may run ahead of the compute warps
+constexpr int kTaskQueue = 8;    // task descriptors the loader may run ahead of the compute warps
+constexpr int kBatch = 8;        // tickets drawn at a time by a loader (a power of two <= 32)
 constexpr unsigned kFullMask = 0xffffffffu;
 
 enum : uint32_t { REC_NOP = 0, REC_BEGIN_RHS, REC_BEGIN_ZERO, REC_BEGIN_SLOT, REC_ADD_SLOT, REC_BLOCK_D4, REC_BLOCK_D1,
@@ -322,8 +323,6 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
     uint32_t j_rel = 0;       // staged records known to be released by the compute warps
     int rows_in_flight = 0;   // ring rows of records j_rel .. j_issue - 1
     int head = 0;             // ring row the next record starts at
-    int t_next = 0;
-    if (lane == 0) t_next = atomicAdd(a.ticket, 1);
 
     // n consecutive rows (row_bytes each, contiguous in global memory) -> ring rows slot, slot + 1, ...
     auto copy_rows = [&](int slot, const F *src, int n, uint64_t *bar) {
@@ -346,47 +345,99 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
         return 0u;
     };
 
-    for (uint32_t q = 0;; ++q) {
-        // ---- next task descriptor -> queue --------------------------------------------------------
-        int ticket = 0, task = 0;
-        uint32_t total = 0, off_lo = 0, off_hi = 0;
-        if (lane == 0) {
-            ticket = t_next;
-            if (ticket < a.n_tasks) {
-                const SweepTask td = a.tasks[ticket];
-                task = (int) td.level, total = td.bytes, off_lo = (uint32_t) td.offset, off_hi = (uint32_t) (td.offset >> 32);
-                t_next = atomicAdd(a.ticket, 1);  // in flight while this task is staged
+    // Tickets are drawn kBatch at a time (consecutive, processed in order: forward progress is unaffected), so the
+    // descriptor fetch costs one round trip per batch and the slab pages of the batch's later tasks are
+    // already in flight while its earlier tasks are staged: per-task latency of the loader is what bounds
+    // the throughput of small tasks.
+    uint32_t q = 0;            // tasks queued so far
+    int t0 = 0;                // first ticket of the current batch
+    if (lane == 0) t0 = atomicAdd(a.ticket, 1);
+    for (;;) {
+        t0 = __shfl_sync(kFullMask, t0, 0);
+        if (t0 >= a.n_tasks) {
+            if (lane == 0) {
+                if (q >= kTaskQueue) mbar_wait(sm.tempty + q % kTaskQueue, ((q / kTaskQueue) - 1) & 1);
+                sm.queue[q % kTaskQueue] = QueuedTask{a.n_tasks, 0, 0u, 0u, 0ull, 0ull};
+                mbar_arrive(sm.tfull + q % kTaskQueue);
             }
+            break;
+        }
+        // The descriptor of the first task says how many tickets may be drawn together here (bits 28-30 of
+        // `bytes`, set by the host: > 1 only deep inside a wide dependency level, where every worker is busy with
+        // tasks of that level anyway; near narrow levels one ticket at a time keeps the critical path short).
+        SweepTask td{0ull, 0u, 0u};
+        if (lane == 0) td = a.tasks[t0];
+        const int hint = (int) ((__shfl_sync(kFullMask, td.bytes, 0) >> 28) & 7u) + 1;
+        int t1 = 0;
+        if (hint > 1) {
+            if (lane == 0) t1 = atomicAdd(a.ticket, hint - 1);
+            t1 = __shfl_sync(kFullMask, t1, 0);
+        }
+        const int my_ticket = lane == 0 ? t0 : t1 + lane - 1;
+        const bool valid = lane < hint && my_ticket < a.n_tasks;
+        if (lane > 0 && valid) td = a.tasks[my_ticket];
+        td.bytes &= 0x0fffffffu;
+        if (!valid) td.bytes = 0;
+        const int n_batch = __popc(__ballot_sync(kFullMask, valid));
+        int t_ahead = a.n_tasks;
+        if (lane == 0) t_ahead = atomicAdd(a.ticket, 1);  // first ticket of the next batch: in flight during this one
+        const uint32_t my_pages = (td.bytes + kPage - 1) / kPage;
+        uint32_t my_first = my_pages;  // inclusive scan ...
+#pragma unroll
+        for (int o = 1; o < kBatch; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(kFullMask, my_first, o);
+            if (lane >= o) my_first += up;
+        }
+        const uint32_t batch_pages = __shfl_sync(kFullMask, my_first, kBatch - 1);
+        my_first = gpage + my_first - my_pages;  // ... made exclusive and global
+        const uint32_t batch_end = gpage + batch_pages;
+        int iss_task = 0;  // batch task owning page `issued` (warp-uniform)
+        // hands pages to TMA in global order while the ring has room: up to page g + kStages - 1; blocks only for page g
+        auto feed_pages = [&](uint32_t g) {
+            const uint32_t limit = min(batch_end, g + kStages);
+            while (issued < limit) {
+                while (issued >= __shfl_sync(kFullMask, my_first + my_pages, iss_task)) iss_task += 1;
+                const uint32_t st = issued % kStages, fill = issued / kStages;
+                if (fill > 0) {
+                    if (issued == g) {
+                        mbar_wait(sm.empty + st, (fill - 1) & 1);
+                    } else {
+                        const int free_now = lane == 0 ? (int) mbar_test(sm.empty + st, (fill - 1) & 1) : 0;
+                        if (!__shfl_sync(kFullMask, free_now, 0)) break;
+                    }
+                }
+                const uint32_t first = __shfl_sync(kFullMask, my_first, iss_task);
+                const uint32_t tbytes = __shfl_sync(kFullMask, td.bytes, iss_task);
+                const uint32_t lo = __shfl_sync(kFullMask, (uint32_t) td.offset, iss_task);
+                const uint32_t hi = __shfl_sync(kFullMask, (uint32_t) (td.offset >> 32), iss_task);
+                const uint32_t pi = issued - first;
+                const uint32_t bytes = min((uint32_t) kPage, tbytes - pi * kPage);
+                if (lane == 0) {
+                    mbar_expect_tx(sm.full + st, bytes);
+                    tma_load_1d(sm.slab + (size_t) st * kPage,
+                                a.slab + ((unsigned long long) lo | (unsigned long long) hi << 32) + (size_t) pi * kPage, bytes, sm.full + st);
+                }
+                issued += 1;
+            }
+        };
+      for (int bi = 0; bi < n_batch; ++bi, ++q) {
+        // ---- task descriptor -> queue ---------------------------------------------------------------
+        const int task = (int) __shfl_sync(kFullMask, td.level, bi);
+        const uint32_t total = __shfl_sync(kFullMask, td.bytes, bi);
+        const uint32_t off_lo = __shfl_sync(kFullMask, (uint32_t) td.offset, bi);
+        const uint32_t off_hi = __shfl_sync(kFullMask, (uint32_t) (td.offset >> 32), bi);
+        const uint32_t task_first = __shfl_sync(kFullMask, my_first, bi);
+        const int ticket = __shfl_sync(kFullMask, my_ticket, bi);
+        if (lane == 0) {
             if (q >= kTaskQueue) mbar_wait(sm.tempty + q % kTaskQueue, ((q / kTaskQueue) - 1) & 1);
             sm.queue[q % kTaskQueue] = QueuedTask{ticket, task, total, 0u, (unsigned long long) off_lo | (unsigned long long) off_hi << 32, 0ull};
             mbar_arrive(sm.tfull + q % kTaskQueue);
         }
-        ticket = __shfl_sync(kFullMask, ticket, 0);
-        if (ticket >= a.n_tasks) break;
-        total = __shfl_sync(kFullMask, total, 0);
-        off_lo = __shfl_sync(kFullMask, off_lo, 0);
-        off_hi = __shfl_sync(kFullMask, off_hi, 0);
-        const unsigned char *base = a.slab + ((unsigned long long) off_lo | (unsigned long long) off_hi << 32);
         const uint32_t n_pages = (total + kPage - 1) / kPage;
 
         for (uint32_t pg = 0; pg < n_pages; ++pg) {
-            const uint32_t g = gpage + pg, stage = g % kStages;
-            if (lane == 0) {
-                // keep the page ring full: pages g .. g + kStages - 1 may be resident; only page g is waited for
-                const uint32_t limit = min(gpage + n_pages, g + kStages);
-                while (issued < limit) {
-                    const uint32_t st = issued % kStages, fill = issued / kStages;
-                    if (fill > 0) {
-                        if (issued == g) mbar_wait(sm.empty + st, (fill - 1) & 1);
-                        else if (!mbar_test(sm.empty + st, (fill - 1) & 1)) break;
-                    }
-                    const uint32_t pi = issued - gpage;
-                    const uint32_t bytes = min((uint32_t) kPage, total - pi * kPage);
-                    mbar_expect_tx(sm.full + st, bytes);
-                    tma_load_1d(sm.slab + (size_t) st * kPage, base + (size_t) pi * kPage, bytes, sm.full + st);
-                    issued += 1;
-                }
-            }
+            const uint32_t g = task_first + pg, stage = g % kStages;
+            feed_pages(g);
             __syncwarp();
             mbar_wait(sm.full + stage, (g / kStages) & 1);
             const unsigned char *p = sm.slab + (size_t) stage * kPage;
@@ -511,7 +562,9 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
             __syncwarp();  // every lane is done reading this stage
             if (lane == 0) mbar_arrive(sm.empty + stage);
         }
-        gpage += n_pages;
+      }
+        gpage = batch_end;
+        t0 = t_ahead;
     }
 }
 
