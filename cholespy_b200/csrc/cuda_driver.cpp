@@ -41,6 +41,13 @@ CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, u
 CUresult (*cuLaunchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                                       CUstream, void **) = nullptr;
 CUresult (*cuStreamSynchronize)(CUstream) = nullptr;
+CUresult (*cuStreamCreate)(CUstream *, unsigned int) = nullptr;
+CUresult (*cuStreamDestroy)(CUstream) = nullptr;
+CUresult (*cuStreamWaitEvent)(CUstream, CUevent, unsigned int) = nullptr;
+CUresult (*cuEventCreate)(CUevent *, unsigned int) = nullptr;
+CUresult (*cuEventDestroy)(CUevent) = nullptr;
+CUresult (*cuEventRecord)(CUevent, CUstream) = nullptr;
+CUresult (*cuMemcpy2DAsync)(const CUDA_MEMCPY2D *, CUstream) = nullptr;
 CUresult (*cuPointerGetAttribute)(void *, int, CUdeviceptr) = nullptr;
 
 CUdevice cu_device = 0;
@@ -93,7 +100,10 @@ bool load_symbols() {
               resolve(cuOccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor") &&
               resolve(cuLaunchKernel, "cuLaunchKernel") &&
               resolve(cuLaunchCooperativeKernel, "cuLaunchCooperativeKernel") &&
-              resolve(cuStreamSynchronize, "cuStreamSynchronize") &&
+              resolve(cuStreamSynchronize, "cuStreamSynchronize") && resolve(cuStreamCreate, "cuStreamCreate") &&
+              resolve(cuStreamDestroy, "cuStreamDestroy_v2") && resolve(cuStreamWaitEvent, "cuStreamWaitEvent") &&
+              resolve(cuEventCreate, "cuEventCreate") && resolve(cuEventDestroy, "cuEventDestroy_v2") &&
+              resolve(cuEventRecord, "cuEventRecord") && resolve(cuMemcpy2DAsync, "cuMemcpy2DAsync_v2") &&
               resolve(cuPointerGetAttribute, "cuPointerGetAttribute");
     if (!ok) return false;
     CUresult rc = cuInit(0);

@@ -23,6 +23,23 @@ using CUresult = int;
 using CUdevice = int;
 using CUdeviceptr = void *;
 
+// cuMemcpy2DAsync descriptor (driver ABI layout of CUDA_MEMCPY2D; memory types: 1 = host, 2 = device)
+struct CUDA_MEMCPY2D {
+    size_t srcXInBytes, srcY;
+    unsigned int srcMemoryType;
+    const void *srcHost;
+    CUdeviceptr srcDevice;
+    void *srcArray;
+    size_t srcPitch;
+    size_t dstXInBytes, dstY;
+    unsigned int dstMemoryType;
+    void *dstHost;
+    CUdeviceptr dstDevice;
+    void *dstArray;
+    size_t dstPitch;
+    size_t WidthInBytes, Height;
+};
+
 // -- entry points (resolved by init_cuda) ---------------------------------------------------------
 extern CUresult (*cuInit)(unsigned int);
 extern CUresult (*cuDeviceGet)(CUdevice *, int);
@@ -53,6 +70,13 @@ extern CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsi
 extern CUresult (*cuLaunchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                                              unsigned, CUstream, void **);
 extern CUresult (*cuStreamSynchronize)(CUstream);
+extern CUresult (*cuStreamCreate)(CUstream *, unsigned int);
+extern CUresult (*cuStreamDestroy)(CUstream);
+extern CUresult (*cuStreamWaitEvent)(CUstream, CUevent, unsigned int);
+extern CUresult (*cuEventCreate)(CUevent *, unsigned int);
+extern CUresult (*cuEventDestroy)(CUevent);
+extern CUresult (*cuEventRecord)(CUevent, CUstream);
+extern CUresult (*cuMemcpy2DAsync)(const CUDA_MEMCPY2D *, CUstream);
 extern CUresult (*cuPointerGetAttribute)(void *, int, CUdeviceptr);
 
 #define cuda_check(err) cuda_check_impl(err, __FILE__, __LINE__)

@@ -292,6 +292,14 @@ GpuSolver::~GpuSolver() {
     dev_free(m_rbuf);
     dev_free(m_stage_b);
     dev_free(m_stage_x);
+    if (m_copy_in) {
+        cuda_check(cuStreamDestroy(m_copy_in));
+        cuda_check(cuStreamDestroy(m_copy_out));
+        for (int i = 0; i < 4; ++i) {
+            cuda_check(cuEventDestroy(m_ev_in[i]));
+            cuda_check(cuEventDestroy(m_ev_out[i]));
+        }
+    }
 }
 
 ImageShape GpuSolver::shape() const {
@@ -381,13 +389,16 @@ void GpuSolver::solve(int k, const void *b, void *x) {
     }
     ContextGuard guard(m_dev);
     if (k != m_k) {
-        dev_free(m_tmp);
-        dev_free(m_scratch);
-        dev_free(m_rbuf);
-        m_rbuf = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) padded_rhs(k));
-        m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) padded_rhs(k));
-        const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
-        m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) padded_rhs(k));
+        if (padded_rhs(k) > m_kp_cap) {  // work buffers grow, never shrink (the kernels address them with round4(k))
+            dev_free(m_tmp);
+            dev_free(m_scratch);
+            dev_free(m_rbuf);
+            m_kp_cap = padded_rhs(k);
+            m_rbuf = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) m_kp_cap);
+            m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) m_kp_cap);
+            const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
+            m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) m_kp_cap);
+        }
         m_k = k;
     }
     m_epoch += 1;
@@ -395,8 +406,18 @@ void GpuSolver::solve(int k, const void *b, void *x) {
     sweep(true, k, nullptr, x);   // x = P' L^-T tmp
 }
 
+// Host buffers end to end.  RHS columns are independent, so for k >= 64 the columns are processed in two (up to
+// four) blocks: the strided H2D copy of block c + 1 (copy stream), the two sweeps of block c (legacy stream) and the
+// D2H copy of block c - 1 (second copy stream) overlap; events order them.  PCIe then runs in both directions
+// while the sweeps execute.
 void GpuSolver::solve_host(int k, const void *b_host, void *x_host) {
-    const size_t bytes = (size_t) m_elem * (size_t) m_n * (size_t) k;
+    if (k > 128) throw std::invalid_argument("The number of RHS should be less than 128.");
+    if (k < 1) throw std::invalid_argument("The number of RHS should be at least 1.");
+    const size_t es = (size_t) m_elem;
+    const size_t bytes = es * (size_t) m_n * (size_t) k;
+    int n_blocks = k >= 64 ? 2 : 1;  // measured on cfg4: 2 blocks of 64 columns beat 4 of 32 (a sweep is latency-bound, not k-bound)
+    if (const char *v = std::getenv("CHB_HOST_BLOCKS")) n_blocks = std::max(1, std::min(std::min(4, k), std::atoi(v)));
+    const int kb = (k + n_blocks - 1) / n_blocks;
     {
         ContextGuard guard(m_dev);
         if (bytes > m_stage_bytes) {
@@ -406,12 +427,63 @@ void GpuSolver::solve_host(int k, const void *b_host, void *x_host) {
             m_stage_x = dev_alloc(bytes);
             m_stage_bytes = bytes;
         }
-        h2d(m_stage_b, b_host, bytes);
+        if (n_blocks == 1) h2d(m_stage_b, b_host, bytes);
+        if (n_blocks > 1 && !m_copy_in) {
+            cuda_check(cuStreamCreate(&m_copy_in, 1));   // CU_STREAM_NON_BLOCKING: no implicit sync with the legacy stream
+            cuda_check(cuStreamCreate(&m_copy_out, 1));
+            for (int i = 0; i < 4; ++i) {
+                cuda_check(cuEventCreate(&m_ev_in[i], 2));   // CU_EVENT_DISABLE_TIMING
+                cuda_check(cuEventCreate(&m_ev_out[i], 2));
+            }
+        }
     }
-    solve(k, m_stage_b, m_stage_x);
+    if (n_blocks == 1) {
+        solve(k, m_stage_b, m_stage_x);
+        ContextGuard guard(m_dev);
+        d2h(x_host, m_stage_x, bytes);
+        sync0();
+        return;
+    }
+    // column block c: columns [c0, c0 + kc) of the row-major (n, k) host arrays <-> a packed (n, kc) device block
+    auto copy_block = [&](bool to_device, int c0, int kc, void *dev, CUstream stream) {
+        CUDA_MEMCPY2D d;
+        std::memset(&d, 0, sizeof d);
+        d.WidthInBytes = es * (size_t) kc;
+        d.Height = (size_t) m_n;
+        if (to_device) {
+            d.srcMemoryType = 1, d.srcHost = b_host, d.srcPitch = es * (size_t) k, d.srcXInBytes = es * (size_t) c0;
+            d.dstMemoryType = 2, d.dstDevice = dev, d.dstPitch = es * (size_t) kc;
+        } else {
+            d.srcMemoryType = 2, d.srcDevice = dev, d.srcPitch = es * (size_t) kc;
+            d.dstMemoryType = 1, d.dstHost = x_host, d.dstPitch = es * (size_t) k, d.dstXInBytes = es * (size_t) c0;
+        }
+        cuda_check(cuMemcpy2DAsync(&d, stream));
+    };
+    std::vector<int> c0s, kcs;
+    for (int c0 = 0; c0 < k; c0 += kb) c0s.push_back(c0), kcs.push_back(std::min(kb, k - c0));
+    {
+        ContextGuard guard(m_dev);
+        for (size_t c = 0; c < c0s.size(); ++c) {
+            void *dev_b = (char *) m_stage_b + es * (size_t) m_n * (size_t) c0s[c];
+            copy_block(true, c0s[c], kcs[c], dev_b, m_copy_in);
+            cuda_check(cuEventRecord(m_ev_in[c], m_copy_in));
+        }
+    }
+    for (size_t c = 0; c < c0s.size(); ++c) {
+        void *dev_b = (char *) m_stage_b + es * (size_t) m_n * (size_t) c0s[c];
+        void *dev_x = (char *) m_stage_x + es * (size_t) m_n * (size_t) c0s[c];
+        {
+            ContextGuard guard(m_dev);
+            cuda_check(cuStreamWaitEvent(nullptr, m_ev_in[c], 0));
+        }
+        solve(kcs[c], dev_b, dev_x);
+        ContextGuard guard(m_dev);
+        cuda_check(cuEventRecord(m_ev_out[c], nullptr));
+        cuda_check(cuStreamWaitEvent(m_copy_out, m_ev_out[c], 0));
+        copy_block(false, c0s[c], kcs[c], dev_x, m_copy_out);
+    }
     ContextGuard guard(m_dev);
-    d2h(x_host, m_stage_x, bytes);
-    sync0();
+    cuda_check(cuStreamSynchronize(m_copy_out));
 }
 
 }  // namespace chb

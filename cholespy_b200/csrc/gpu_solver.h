@@ -113,8 +113,13 @@ private:
     void *m_tmp = nullptr;      // Float[n*k]
     void *m_rbuf = nullptr;     // Float[n*round4(k)]: residuals of the inverse super-blocks
     void *m_scratch = nullptr;  // Float[max n_slots * 16 * k]: parked partial tiles
-    void *m_stage_b = nullptr, *m_stage_x = nullptr;  // device staging for solve_host
+    int m_kp_cap = 0;           // padded RHS width the work buffers are allocated for (grow-only)
+    // solve_host: device staging + two copy streams so that the H2D copy of column block c + 1, the sweeps of
+    // block c and the D2H copy of block c - 1 overlap
+    void *m_stage_b = nullptr, *m_stage_x = nullptr;
     size_t m_stage_bytes = 0;
+    CUstream m_copy_in = nullptr, m_copy_out = nullptr;
+    CUevent m_ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, m_ev_out[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 }  // namespace chb

@@ -227,6 +227,20 @@ def test_solve_host_end_to_end(oracle_mod, native_lib):
     x = np.zeros_like(b)
     s.solve_host(b, x)
     assert max_rel_err(x, oracle_mod.solve(cp, ri, v, perm, b)) < 1e-12
+    # k >= 64 takes the pipelined path (column blocks on copy streams overlapping the sweeps); pinned and pageable hosts
+    for k in (64, 100, 128):
+        b = np.random.default_rng(k).random((p["n"], k))
+        x_ref = oracle_mod.solve(cp, ri, v, perm, b)
+        x = np.zeros_like(b)
+        s.solve_host(b, x)
+        assert max_rel_err(x, x_ref) < 1e-12, k
+        bt = torch.tensor(b).pin_memory()
+        xt = torch.zeros_like(bt).pin_memory()
+        for _ in range(2):  # back to back: the staging buffers are reused
+            s.solve_host(bt, xt)
+        assert max_rel_err(xt.numpy(), x_ref) < 1e-12, k
+        xd = _gpu_solve(s, b)  # device path right after, on the same solver (work buffers are shared)
+        assert max_rel_err(xd, x_ref) < 1e-12, k
 
 
 def test_from_factor_entry_point(oracle_mod, native_lib):
