@@ -211,7 +211,7 @@ def run_reference(args, name, p, k, dtype):
         sample_k, k, len(times), cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
         "config": {"workload": workload_description(name, p, k, dtype), "sample_columns": sample_k},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
@@ -275,7 +275,14 @@ def run_b200(args, name, p, k_total, dtype):
     s = np.dtype(dtype).itemsize
     # RHS-column shard of this rank (columns are independent; no data-path collective)
     from cholespy_b200 import multi_gpu
-    cols = [c for _, c in multi_gpu.column_shards(k_total, world)]
+    # weak (default, tier rule 5): every rank solves the config's k columns of its own (k * N columns per step in
+    # total, no data-path collective); strong: the config's k columns are split over the ranks
+    k_config = k_total
+    if args.scaling == "weak":
+        k_total = k_config * world
+        cols = [k_config] * world
+    else:
+        cols = [c for _, c in multi_gpu.column_shards(k_total, world)]
     k = cols[rank]
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     gen = torch.Generator(device="cpu").manual_seed(45 + rank)
@@ -383,9 +390,12 @@ def run_b200(args, name, p, k_total, dtype):
             cpu_baseline["gpu_vs_oracle_max_rel_err"] = err
         line = {
             "metric": METRIC, "value": k_total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
-            "config": {"workload": workload_description(name, p, k_total, dtype), "n": n, "nnz_l": z, "k_total": k_total,
+            "config": {"workload": workload_description(name, p, k_config, dtype) + (
+                           " per GPU (weak scaling: %d columns per step over %d GPUs)" % (k_total, world) if world > 1 and args.scaling == "weak"
+                           else (" sharded over %d GPUs" % world if world > 1 else "")),
+                       "n": n, "nnz_l": z, "k_total": k_total,
                        "k_per_rank": cols, "levels": list(nlev), "parallelism": "rhs-columns x%d" % world,
                        "l2": "512 MB flush write between timed steps", "grid": info.get("grid")},
             "e2e": {"value": k_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * k * s,
@@ -408,6 +418,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("CHB_WORKLOAD", "cfg4"))
     ap.add_argument("--k", type=int, default=0, help="override the number of RHS columns")
     ap.add_argument("--dtype", default="", choices=["", "f", "d"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU solves the config's RHS columns (default); strong = they are split")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-columns", type=int, default=32, help="columns of the bounded CPU-baseline sample")
     ap.add_argument("--ref-procs", type=int, default=64, help="worker processes of the reference arm (capped at the core count)")
