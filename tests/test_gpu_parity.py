@@ -270,3 +270,40 @@ def test_repeated_solves_are_deterministic_and_linear():
     s32 = _solver(p, np.float32)
     xf = _gpu_solve(s32, b1.astype(np.float32))
     assert max_rel_err(xf, x1) < 1e-5
+
+
+@pytest.mark.parametrize("name,dtype,k", [("grid3d-20", np.float64, 1), ("localspd-120", np.float64, 128),
+                                          ("grid2d-128", np.float64, 1), ("ico6", np.float32, 127), ("ico6", np.float32, 3)])
+def test_baseline_config_shapes_at_reduced_size(name, dtype, k, oracle_mod, native_lib):
+    """The shapes of BASELINE.json's configs (3-D grid CSC f64 k=1, local SPD CSR f64 k=128, 2-D grid COO f64 k=1,
+    icosphere COO f32 k=3 / an odd k whose b rows are not 16-byte multiples) at sizes the oracle solves in seconds."""
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    A = problems.to_scipy_csc(p)
+    b = np.random.default_rng(45).random((p["n"], k)).astype(dtype)
+    s = _solver(p, dtype)
+    x = _gpu_solve(s, b)
+    assert max_rel_err(x, oracle_mod.solve(cp, ri, v, perm, b)) < TOL[np.dtype(dtype)]
+    assert rel_residual(A, x, b) < (1e-5 if dtype == np.float32 else 1e-13)
+    info = s.info()
+    lo_ref = oracle_mod.levels(*oracle_mod.csc_to_csr(cp, ri, v)[:2], False)
+    assert info["n_levels_lower"] == lo_ref[1] and np.array_equal(s.analysis(True)[0], lo_ref[0])
+
+
+def test_degenerate_systems():
+    """Edge cases: a 1 x 1 system, a diagonal matrix (every row in level 0, no blocks at all) and a tridiagonal chain
+    (one row per level: the longest possible dependency chain for its size)."""
+    for n, offdiag in ((1, 0.0), (300, 0.0), (300, -1.0)):
+        main = np.full(n, 4.0)
+        A = sp.diags([main], [0]) if offdiag == 0.0 or n == 1 else sp.diags([np.full(n - 1, offdiag), main, np.full(n - 1, offdiag)], [-1, 0, 1])
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        for dtype in (np.float32, np.float64):
+            Solver = CholeskySolverF if dtype == np.float32 else CholeskySolverD
+            s = Solver(n, torch.tensor(A.indptr.astype(np.int32), device="cuda"), torch.tensor(A.indices.astype(np.int32), device="cuda"),
+                       torch.tensor(A.data.astype(np.float64), device="cuda"), MatrixType.CSC)
+            for k in (1, 7, 128):
+                b = np.random.default_rng(n + k).random((n, k)).astype(dtype)
+                x = _gpu_solve(s, b)
+                x_ref = spsolve(A, b.astype(np.float64)).reshape(n, k)
+                assert max_rel_err(x, x_ref) < (2e-6 if dtype == np.float32 else 1e-13), (n, offdiag, k)
