@@ -187,6 +187,7 @@ struct Builder {
     int loc_lo = 0, loc_n_int = 0;
     std::vector<int> loc_ext;
     // inverse super-blocks: A tasks end by storing the residual instead of solving the triangle
+    std::vector<int> local_root;  // root panel of the local subtree a panel belongs to, or -1
     bool end_store_r = false;
     std::vector<int> atask_of_panel;
 
@@ -492,8 +493,12 @@ struct Builder {
         loc_ext.clear();
         std::vector<uint32_t> waits;
         if (upper) {
-            // every row the subtree reads from outside lies in the below-panel row list of its root
-            loc_ext.assign(S.rows.begin() + S.rlo[hi], S.rows.begin() + S.rlo[hi] + S.m[hi]);
+            // every row a subtree reads from outside lies in the below-panel row list of its root; a task may hold
+            // several adjacent subtrees (a forest): the union over their roots
+            for (int P = lo; P <= hi; ++P)
+                if (local_root[P] == P) loc_ext.insert(loc_ext.end(), S.rows.begin() + S.rlo[P], S.rows.begin() + S.rlo[P] + S.m[P]);
+            std::sort(loc_ext.begin(), loc_ext.end());
+            loc_ext.erase(std::unique(loc_ext.begin(), loc_ext.end()), loc_ext.end());
             for (int r : loc_ext) {
                 const uint32_t code = wait_code(task_of_panel[S.panel_of_row[r]]);
                 if (code && std::find(waits.begin(), waits.end(), code) == waits.end()) waits.push_back(code);
@@ -561,6 +566,40 @@ struct Builder {
             if (contiguous && rows <= max_rows && S.m[P] <= opt.local_ext && rows + S.m[P] <= 255 && sub_cost[P] <= opt.local_cost)
                 for (int q = first[P]; q <= P; ++q) root_of[q] = P;
         }
+        // Adjacent local subtrees (consecutive in the postorder, hence independent of each other) are merged into one
+        // task while the row / external-row / cost budgets allow: the fixed cost of a task (ticket, queue, slab page,
+        // publish) is several times the arithmetic of a 5-row subtree.
+        local_root = root_of;
+        std::vector<int> group_lo(np, -1), group_hi(np, -1);
+        {
+            int P = 0;
+            while (P < np) {
+                if (root_of[P] < 0) {
+                    ++P;
+                    continue;
+                }
+                const int g_lo = P;
+                int g_hi = root_of[P];
+                int64_t g_cost = sub_cost[g_hi];
+                std::vector<int> ext(S.rows.begin() + S.rlo[g_hi], S.rows.begin() + S.rlo[g_hi] + S.m[g_hi]), merged;
+                while (g_hi + 1 < np && root_of[g_hi + 1] >= 0) {
+                    const int r2 = root_of[g_hi + 1];
+                    const int rows = S.c0[r2 + 1] - S.c0[g_lo];
+                    merged.clear();
+                    std::set_union(ext.begin(), ext.end(), S.rows.begin() + S.rlo[r2], S.rows.begin() + S.rlo[r2] + S.m[r2],
+                                   std::back_inserter(merged));
+                    if (rows > max_rows || (int) merged.size() > opt.local_ext || rows + (int) merged.size() > 255 ||
+                        g_cost + sub_cost[r2] > opt.local_cost)
+                        break;
+                    ext.swap(merged);
+                    g_cost += sub_cost[r2];
+                    g_hi = r2;
+                }
+                for (int q = g_lo; q <= g_hi; ++q) group_lo[q] = g_lo, group_hi[q] = g_hi;
+                P = g_hi + 1;
+            }
+        }
+
         // Inverse super-blocks: runs of <= inv_panels consecutive panels of one supernode (outside local tasks)
         std::vector<int> sb_lo(np, -1), sb_hi(np, -1);
         if (!opt.exact_order && opt.inv_panels >= 2) {
@@ -652,11 +691,12 @@ struct Builder {
             int lo, hi;
             if (!upper) {
                 lo = i;
-                hi = root_of[i] >= 0 ? root_of[i] : i;
+                hi = root_of[i] >= 0 ? group_hi[i] : i;
+                if (root_of[i] >= 0 && group_lo[i] != i) throw std::logic_error("panel schedule: local task is not contiguous");
             } else {
                 hi = np - 1 - i;
-                lo = root_of[hi] >= 0 ? first[hi] : hi;
-                if (root_of[hi] >= 0 && root_of[hi] != hi) throw std::logic_error("panel schedule: local subtree is not contiguous");
+                lo = root_of[hi] >= 0 ? group_lo[hi] : hi;
+                if (root_of[hi] >= 0 && group_hi[hi] != hi) throw std::logic_error("panel schedule: local task is not contiguous");
             }
             i += hi - lo + 1;
             if (root_of[hi] >= 0) {
