@@ -484,6 +484,68 @@ struct Builder {
         close_task();
     }
 
+    // The rows of a local task as plain sparse rows (REC_LOCAL_ROWS): at the bottom of the elimination tree rows hold
+    // a handful of non-zeros, and a row-by-row substitution out of shared memory costs a fraction of the panel /
+    // block machinery.  Forward: row i of L, ascending columns; backward: column j of L (row j of L'), descending
+    // rows -- the reference's summation orders.  Entries come in groups of 4 (zero padding is bit-neutral).
+    void emit_local_rows(int lo, int hi) {
+        const int n_int = loc_n_int, c_lo = loc_lo;
+        struct Entry {
+            int idx;
+            double v;
+        };
+        std::vector<std::vector<Entry>> rows((size_t) n_int);
+        std::vector<double> diag((size_t) n_int);
+        for (int j = 0; j < n_int; ++j) {
+            const int c = c_lo + j;
+            diag[j] = L.vals[(size_t) L.colptr[c]];
+            if (!upper) {
+                for (int e = L.colptr[c] + 1; e < L.colptr[c + 1] && L.rowidx[e] < c_lo + n_int; ++e)
+                    rows[(size_t) (L.rowidx[e] - c_lo)].push_back(Entry{j, L.vals[(size_t) e]});  // ascending columns per row
+            } else {
+                for (int e = L.colptr[c + 1] - 1; e > L.colptr[c]; --e)
+                    rows[j].push_back(Entry{local_index(L.rowidx[e]), L.vals[(size_t) e]});       // descending rows
+            }
+        }
+        (void) lo, (void) hi;
+        const size_t es = (size_t) img.elem;
+        auto row_bytes = [&](int j) {
+            const size_t n4 = (rows[j].size() + 3) / 4;
+            return 16 + round16(4 * n4) + 4 * n4 * es;
+        };
+        int j = 0;
+        while (j < n_int) {
+            // as many rows as fit one page (a record never straddles a page)
+            size_t bytes = 0;
+            int cnt = 0;
+            while (j + cnt < n_int && 16 + bytes + row_bytes(upper ? n_int - 1 - (j + cnt) : j + cnt) <= (size_t) img.page_bytes) {
+                bytes += row_bytes(upper ? n_int - 1 - (j + cnt) : j + cnt);
+                cnt += 1;
+            }
+            if (cnt == 0) throw std::logic_error("panel schedule: a local row does not fit a page");
+            const size_t off = w.record(REC_LOCAL_ROWS, cnt, opt.exact_order ? 0u : 1u, 0, bytes);
+            size_t at = off;
+            for (int q = 0; q < cnt; ++q) {
+                const int r = upper ? n_int - 1 - (j + q) : j + q;
+                const std::vector<Entry> &ent = rows[(size_t) r];
+                const size_t n4 = (ent.size() + 3) / 4;
+                if (n4 > 255) throw std::logic_error("panel schedule: local row too long");
+                w.put_int(at, 0, (int32_t) ((uint32_t) r | (uint32_t) n4 << 8));
+                // the pivot at byte 8: reciprocal in fast mode (multiply), the diagonal itself in exact-order mode (IEEE divide)
+                w.put_value(at + 8, 0, opt.exact_order ? diag[(size_t) r] : 1.0 / diag[(size_t) r]);
+                uint8_t idx[1024];
+                for (size_t i = 0; i < 4 * n4; ++i) idx[i] = (uint8_t) (i < ent.size() ? ent[i].idx : r);
+                w.put_bytes(at + 16, idx, 4 * n4);
+                const size_t voff = at + 16 + round16(4 * n4);
+                for (size_t i = 0; i < ent.size(); ++i) w.put_value(voff, i, ent[i].v);
+                at = voff + 4 * n4 * es;
+                img.n_values += (int64_t) ent.size() + 1;
+                img.n_stored_values += (int64_t) (4 * n4) + 1;
+            }
+            j += cnt;
+        }
+    }
+
     // One LOCAL task: the complete subtree of panels [lo, hi] (hi = its root), solved in shared memory.
     void emit_local_task(int lo, int hi, std::vector<int64_t> &blocks) {
         open_task();
@@ -517,13 +579,9 @@ struct Builder {
                 for (int i = 0; i < loc_n_int; ++i) w.put_int(off, (size_t) i, L.perm[loc_lo + i]);
             }
         }
-        for (int c = 0; c <= hi - lo; ++c) {
-            const int P = upper ? hi - c : lo + c;
-            blocks_of(P, blocks);
-            emit_begin_rhs(P);
-            for (int64_t b : blocks) emit_block(P, b);
-            emit_end_final(P);
-        }
+        (void) blocks;
+        emit_local_rows(lo, hi);
+        for (int P = lo; P <= hi; ++P) task_of_panel[P] = cur;
         {
             const size_t off = w.record(REC_LOCAL_STORE, loc_lo, (uint32_t) loc_n_int, 0, upper ? 4 * pad4(loc_n_int) : 0);
             if (upper)

@@ -77,6 +77,10 @@ enum RecordType : uint32_t {
                          // local[n_int + e] = tmp[ext_row[e]] after every wait code has published
     REC_LOCAL_STORE = 12,// a = row_lo, b = n_int.  payload backward: perm[n_int].  tmp[row_lo + i] = local[i]
                          // (backward: also x[perm[i]] = local[i]); the task's last record
+    REC_LOCAL_ROWS = 14, // a = n_rows, b = 1: pivots are reciprocals (multiply) / 0: diagonals (divide).  The rows of a local task
+                         // as sparse rows, in sweep order; per row: 16-byte header {u32 local_row | n4 << 8, pad, pivot at
+                         // byte 8}, 4 n4 local source indices (u8, padded to 16 bytes), 4 n4 values:
+                         // local[row] = (local[row] - sum values[i] * local[idx[i]]) * or / pivot
     REC_END_STORE = 13,  // a = row0, b = w, c = destination: 0 = the work vector (payload backward: perm[16]; publishes the
                          // panel), 1 = the residual vector r of an inverse super-block.  No triangle.
     REC_SRC_R_FLAG = 0x80, // on a BLOCK record: the source rows are rows of the residual vector r, not of the work vector

@@ -62,7 +62,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 enum : uint32_t { REC_NOP = 0, REC_BEGIN_RHS, REC_BEGIN_ZERO, REC_BEGIN_SLOT, REC_ADD_SLOT, REC_BLOCK_D4, REC_BLOCK_D1,
                   REC_BLOCK_TM, REC_END_FINAL, REC_END_SLOT, REC_END_DENSE, REC_LOCAL_LOAD, REC_LOCAL_STORE,
-                  REC_END_STORE, REC_LOCAL_FLAG = 0x40, REC_SRC_R_FLAG = 0x80 };
+                  REC_END_STORE, REC_LOCAL_ROWS, REC_LOCAL_FLAG = 0x40, REC_SRC_R_FLAG = 0x80 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -217,28 +217,21 @@ struct QueuedTask {
 
 // One block record: tile -= L_block * sources ("grouped source-major" values, panel_schedule.h).  `ring`
 // points at this lane's column of ring row 0 (rows are kp elements apart, the ring has ring_rows rows).
-// The record's rows start at ring row `base`:
-//   STAGED: the ns source rows in ASCENDING row order (the backward sweep visits them descending);
-//   LOCAL:  the rows of the whole local task; idx (16 bytes in front of the values) = local index per source.
-// A plain loop on purpose (small instruction footprint); two sources per iteration hide the LDS latency.
-template <typename F, bool LOCAL, bool UPPER>
+// The record's ns source rows start at ring row `base`, in ASCENDING row order (the backward sweep visits them
+// descending).  A plain loop on purpose (small instruction footprint); two sources per iteration hide the LDS latency.
+template <typename F, bool UPPER>
 __device__ __forceinline__ void run_block(F (&T)[W], uint32_t masks, const unsigned char *pay, const F *ring, int kp, int base) {
     const uint32_t tmask = masks >> 16;
     const int ns = __popc(masks & 0xffff);
     const bool g0 = (tmask & 0x000f) != 0, g1 = (tmask & 0x00f0) != 0, g2 = (tmask & 0x0f00) != 0, g3 = (tmask & 0xf000) != 0;
     const int stride = 4 * ((int) g0 + (int) g1 + (int) g2 + (int) g3);
-    const F *val = reinterpret_cast<const F *>(pay + (LOCAL ? 16 : 0));
+    const F *val = reinterpret_cast<const F *>(pay);
     // a record's rows are contiguous in the ring (the loader never lets one wrap around)
-    const F *src = ring + (size_t) (UPPER && !LOCAL ? base + ns - 1 : base) * kp;
+    const F *src = ring + (size_t) (UPPER ? base + ns - 1 : base) * kp;
 #pragma unroll 2
     for (int r = 0; r < ns; ++r) {
-        F x;
-        if (LOCAL) {
-            x = src[(size_t) pay[r] * kp];
-        } else {
-            x = *src;
-            src = UPPER ? src - kp : src + kp;
-        }
+        const F x = *src;
+        src = UPPER ? src - kp : src + kp;
         const F *v = val;
         if (g0) {
             const Vec4<F> vv = Vec4<F>::load(v);
@@ -667,45 +660,51 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
             while (p < pend) {
                 const uint4 h = *reinterpret_cast<const uint4 *>(p);
                 const uint32_t type = h.x & 0x3f;
-                const bool local = (h.x & REC_LOCAL_FLAG) != 0;
                 const unsigned char *pay = p + 16;
                 p += (h.x >> 8) * 16;
                 if (type == REC_BLOCK_D4) {
-                    if (local) {
-                        run_block<F, true, UPPER>(T, h.z, pay, ring, kp, lbase);
-                    } else {
-                        const int base = acquire_rows(__popc(h.z & 0xffff));
-                        run_block<F, false, UPPER>(T, h.z, pay, ring, kp, base);
-                        release_rows(__popc(h.z & 0xffff));
+                    const int base = acquire_rows(__popc(h.z & 0xffff));
+                    run_block<F, UPPER>(T, h.z, pay, ring, kp, base);
+                    release_rows(__popc(h.z & 0xffff));
+                } else if (type == REC_LOCAL_ROWS) {
+                    // the rows of a local task as sparse rows, substituted in place in the ring (each lane its own column)
+                    F *lrow = ring + (size_t) lbase * kp;
+                    const unsigned char *q = pay;
+                    for (int i = 0; i < (int) h.y; ++i) {
+                        const uint32_t meta = *reinterpret_cast<const uint32_t *>(q);
+                        const F pivot = *reinterpret_cast<const F *>(q + 8);
+                        const int n4 = (int) (meta >> 8 & 0xff);
+                        const unsigned char *idx = q + 16;
+                        const F *val = reinterpret_cast<const F *>(q + 16 + ((4 * n4 + 15) & ~15));
+                        F *dst = lrow + (size_t) (meta & 0xff) * kp;
+                        F acc = *dst;
+                        for (int g = 0; g < n4; ++g) {
+                            const uint32_t i4 = *reinterpret_cast<const uint32_t *>(idx + 4 * g);
+                            const Vec4<F> vv = Vec4<F>::load(val + 4 * g);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc = fnma(vv.x[j], lrow[(size_t) (i4 >> (8 * j) & 0xff) * kp], acc);
+                        }
+                        acc = EXACT ? acc / pivot : acc * pivot;
+                        if (active) *dst = acc;
+                        q = reinterpret_cast<const unsigned char *>(val + 4 * n4);
                     }
                 } else if (type == REC_BEGIN_RHS) {
                     row0 = (int) h.y;
                     w = (int) h.z;
-                    if (local) {
+                    const int base = acquire_rows(w);
 #pragma unroll
-                        for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(lbase, row0 + i) : F(0);
-                    } else {
-                        const int base = acquire_rows(w);
-#pragma unroll
-                        for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(base, i) : F(0);
-                        release_rows(w);
-                    }
+                    for (int i = 0; i < W; ++i) T[i] = i < w ? ring_at(base, i) : F(0);
+                    release_rows(w);
                 } else if (type == REC_END_DENSE || type == REC_END_FINAL || type == REC_END_STORE) {
-                    // (triangle,) then the tile goes to its local rows, to the residual vector, or to the work vector
+                    // (triangle,) then the tile goes to the residual vector or to the work vector
                     // (and, backward, through P' to x): one copy of the store code for all of them
                     const int *perm = reinterpret_cast<const int *>(pay);
                     const bool to_residual = type == REC_END_STORE && h.w == 1;
                     if (type != REC_END_STORE) {
-                        const F *m = reinterpret_cast<const F *>(pay + (UPPER && !local ? 4 * W : 0));
+                        const F *m = reinterpret_cast<const F *>(pay + (UPPER ? 4 * W : 0));
                         if (EXACT) tri_exact(m); else tri_fast(m);
                     }
-                    if (local) {
-                        if (active) {
-#pragma unroll
-                            for (int i = 0; i < W; ++i)
-                                if (i < w) ring_at(lbase, row0 + i) = T[i];
-                        }
-                    } else if (active) {
+                    if (active) {
                         F *out = (to_residual ? a.rbuf : a.tmp) + (size_t) row0 * kp + col;
                         const bool scatter = UPPER && !to_residual;
 #pragma unroll

@@ -26,7 +26,7 @@ inline double fnma(double a, double b, double c) { return __builtin_fma(-a, b, c
 inline int span16(uint32_t m) { return m ? 32 - __builtin_clz(m) : 0; }
 
 enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT, END_DENSE,
-       LOCAL_LOAD, LOCAL_STORE, END_STORE, LOCAL_FLAG = 0x40, SRC_R_FLAG = 0x80 };
+       LOCAL_LOAD, LOCAL_STORE, END_STORE, LOCAL_ROWS, LOCAL_FLAG = 0x40, SRC_R_FLAG = 0x80 };
 
 // returns 0, or a negative error code
 template <typename F>
@@ -84,6 +84,30 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                             for (int c = 0; c < k; ++c) loc[(size_t) i * k + c] = tmp[(size_t) (lo + i) * k + c];
                         for (int e = 0; e < n_ext; ++e)
                             for (int c = 0; c < k; ++c) loc[(size_t) (n_int + e) * k + c] = tmp[(size_t) list[e] * k + c];
+                    }
+                } break;
+                case LOCAL_ROWS: {
+                    const int n_rows = (int) h[1];
+                    const bool reciprocal = h[2] == 1;
+                    const uint8_t *q = pay;
+                    for (int i = 0; i < n_rows; ++i) {
+                        uint32_t meta;
+                        std::memcpy(&meta, q, 4);
+                        const int row = (int) (meta & 0xff), n4 = (int) (meta >> 8 & 0xff);
+                        F piv;
+                        std::memcpy(&piv, q + 8, sizeof(F));
+                        const uint8_t *idx = q + 16;
+                        const F *val = (const F *) (q + 16 + ((4 * n4 + 15) & ~15));
+                        if (row >= loc_rows) return -7;
+                        for (int c = 0; c < k; ++c) {
+                            F acc = loc[(size_t) row * k + c];
+                            for (int e = 0; e < 4 * n4; ++e) {
+                                if ((int) idx[e] >= loc_rows) return -7;
+                                acc = fnma(val[e], loc[(size_t) idx[e] * k + c], acc);
+                            }
+                            loc[(size_t) row * k + c] = reciprocal ? acc * piv : acc / piv;
+                        }
+                        q = (const uint8_t *) (val + 4 * n4);
                     }
                 } break;
                 case LOCAL_STORE: {
