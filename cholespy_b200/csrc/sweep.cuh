@@ -502,7 +502,9 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     // are accounted to this record).  Back-pressure: a free barrier pair and enough free rows.
                     int skipped = 0;
                     if (head + nr > ring_rows) skipped = ring_rows - head, head = 0;
-                    while (j_issue - j_rel >= (uint32_t) kRowBars || rows_in_flight + nr + skipped > ring_rows) {
+                    // (The row count is conservative -- a skipped tail counts as occupied -- so with nothing in flight the
+                    // record is always admitted: nr <= ring_rows by construction, and waiting could never end.)
+                    while (j_issue - j_rel >= (uint32_t) kRowBars || (rows_in_flight > 0 && rows_in_flight + nr + skipped > ring_rows)) {
                         mbar_wait(sm.rempty + j_rel % kRowBars, (j_rel / kRowBars) & 1);
                         rows_in_flight -= sm.rows_of[j_rel % kRowBars];
                         j_rel += 1;
