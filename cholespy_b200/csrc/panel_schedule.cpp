@@ -615,13 +615,14 @@ struct Builder {
             sub_count[q] += sub_count[P];
             first[q] = std::min(first[q], first[P]);
         }
-        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 16 : 32);
+        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 16 : 48);
+        const int max_ext = opt.local_ext > 0 ? opt.local_ext : (img.elem == 8 ? 16 : 31);  // <= 31: one loader lane per external row
         std::vector<int> root_of(np, -1);  // root of the local task a panel belongs to, or -1
         for (int P = np - 1; P >= 0; --P) {
             if (root_of[P] >= 0) continue;  // already inside a local subtree
             const bool contiguous = sub_count[P] == P - first[P] + 1;
             const int rows = S.c0[P + 1] - S.c0[first[P]];
-            if (contiguous && rows <= max_rows && S.m[P] <= opt.local_ext && rows + S.m[P] <= 255 && sub_cost[P] <= opt.local_cost)
+            if (contiguous && rows <= max_rows && S.m[P] <= max_ext && rows + S.m[P] <= 255 && sub_cost[P] <= opt.local_cost)
                 for (int q = first[P]; q <= P; ++q) root_of[q] = P;
         }
         // Adjacent local subtrees (consecutive in the postorder, hence independent of each other) are merged into one
@@ -646,7 +647,7 @@ struct Builder {
                     merged.clear();
                     std::set_union(ext.begin(), ext.end(), S.rows.begin() + S.rlo[r2], S.rows.begin() + S.rlo[r2] + S.m[r2],
                                    std::back_inserter(merged));
-                    if (rows > max_rows || (int) merged.size() > opt.local_ext || rows + (int) merged.size() > 255 ||
+                    if (rows > max_rows || (int) merged.size() > max_ext || rows + (int) merged.size() > 255 ||
                         g_cost + sub_cost[r2] > opt.local_cost)
                         break;
                     ext.swap(merged);
