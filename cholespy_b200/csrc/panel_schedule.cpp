@@ -2,6 +2,7 @@
 #include "panel_schedule.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -188,6 +189,7 @@ struct Builder {
     std::vector<int> loc_ext;
     // inverse super-blocks: A tasks end by storing the residual instead of solving the triangle
     std::vector<int> local_root;  // root panel of the local subtree a panel belongs to, or -1
+    int64_t stat_blocks_from_local = 0, stat_rows_from_local = 0, stat_vals_from_local = 0, stat_blocks_nonlocal = 0, stat_rows_nonlocal = 0, stat_ext_rows = 0;
     bool end_store_r = false;
     std::vector<int> atask_of_panel;
 
@@ -338,6 +340,8 @@ struct Builder {
         const int stride = 4 * ng;
         const uint32_t wait = local ? 0u : wait_code(task_of_panel[upper ? t : p]);
         (void) P;
+        if (!upper && !local && !local_root.empty() && local_root[p] >= 0) stat_blocks_from_local += 1, stat_rows_from_local += ns, stat_vals_from_local += (int64_t) ns * popc16(tmask);
+        if (!upper && !local) stat_blocks_nonlocal += 1, stat_rows_nonlocal += ns;
         const size_t off0 = w.record(REC_BLOCK_D4 | flag(), S.c0[upper ? t : p], smask | tmask << 16, wait,
                                      idx_bytes + es * (size_t) ns * (size_t) stride);
         // backward: sources visited in DESCENDING row order (the reference walks a row of L' from its end backwards)
@@ -567,6 +571,7 @@ struct Builder {
             }
         }
         const int n_ext = (int) loc_ext.size(), n_wait = (int) waits.size();
+        stat_ext_rows += n_ext;
         img.max_local_rows = std::max(img.max_local_rows, loc_n_int + n_ext);
         auto pad4 = [](int v) { return (size_t) ((v + 3) & ~3); };
         {
@@ -791,6 +796,10 @@ void build_sweep_image(const HostFactor &L, const PanelStructure &S, int elem_si
     img.slab.reserve((size_t) ((double) L.nnz() * elem_size * 1.3) + (size_t) S.n_panels * 160 + 4096);
     Builder b(L, S, opt, img);
     b.run();
+    if (std::getenv("CHB_SCHED_STATS"))
+        fprintf(stderr, "[sched %s] non-local blocks %lld (rows %lld), of which from local producers %lld (rows %lld, values %lld); ext rows of local tasks %lld\n",
+                upper ? "bwd" : "fwd", (long long) b.stat_blocks_nonlocal, (long long) b.stat_rows_nonlocal, (long long) b.stat_blocks_from_local,
+                (long long) b.stat_rows_from_local, (long long) b.stat_vals_from_local, (long long) b.stat_ext_rows);
 
     // ticket order: by dependency level, larger slabs first inside a level
     const int nt = (int) img.tasks.size();
