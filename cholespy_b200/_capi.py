@@ -8,7 +8,7 @@ _LIB_PATH = os.path.join(_LIB_DIR, "libcholespy_b200.so")
 OK, ERR_INVALID, ERR_RUNTIME = 0, 1, 2
 F32, F64 = 0, 1
 DEVICE_CPU = -1
-IMAGE_SHAPE_WORDS = 15
+IMAGE_SHAPE_WORDS = 16
 
 _lib = None
 

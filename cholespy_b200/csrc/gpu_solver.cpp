@@ -105,6 +105,7 @@ void ImageShape::to_words(int64_t *w) const {
         w[12 + u] = max_local_rows[u];
     }
     w[14] = exact_order;
+    w[15] = n_contrib_rows;
 }
 ImageShape ImageShape::from_words(const int64_t *w) {
     ImageShape s;
@@ -115,6 +116,7 @@ ImageShape ImageShape::from_words(const int64_t *w) {
         s.max_local_rows[u] = w[12 + u];
     }
     s.exact_order = w[14];
+    s.n_contrib_rows = w[15];
     return s;
 }
 
@@ -147,6 +149,7 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
     d.n_slots = img.n_slots;
     d.n_task_levels = img.n_levels;
     d.max_local_rows = img.max_local_rows;
+    d.n_contrib_rows = img.n_contrib_rows;
     d.n_stored_values = img.n_stored_values;
     allocate_sweep(d);
     // device task table in ticket order; the `level` word carries the task id (its flag index)
@@ -271,6 +274,7 @@ GpuSolver::GpuSolver(int device, int elem_size, const ImageShape &shape)
         allocate_sweep(m_sweep[u]);
     }
     m_exact = shape.exact_order != 0;
+    m_sweep[0].n_contrib_rows = shape.n_contrib_rows;
     m_lower.n_levels = (int) shape.n_levels[0];
     m_upper.n_levels = (int) shape.n_levels[1];
     sync0();
@@ -290,6 +294,7 @@ GpuSolver::~GpuSolver() {
     dev_free(m_tmp);
     dev_free(m_scratch);
     dev_free(m_rbuf);
+    dev_free(m_cbuf);
     dev_free(m_stage_b);
     dev_free(m_stage_x);
     if (m_copy_in) {
@@ -313,6 +318,7 @@ ImageShape GpuSolver::shape() const {
         s.max_local_rows[u] = m_sweep[u].max_local_rows;
     }
     s.exact_order = m_exact ? 1 : 0;
+    s.n_contrib_rows = m_sweep[0].n_contrib_rows;
     s.n_levels[0] = m_lower.n_levels;
     s.n_levels[1] = m_upper.n_levels;
     return s;
@@ -364,6 +370,7 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
         a.dst = (Float *) dst;
         a.scratch = (Float *) m_scratch;
         a.rbuf = (Float *) m_rbuf;
+        a.cbuf = (Float *) m_cbuf;
         a.trace = (unsigned long long *) s.trace;
     };
     SweepArgs<float> a32;
@@ -393,7 +400,9 @@ void GpuSolver::solve(int k, const void *b, void *x) {
             dev_free(m_tmp);
             dev_free(m_scratch);
             dev_free(m_rbuf);
+            dev_free(m_cbuf);
             m_kp_cap = padded_rhs(k);
+            m_cbuf = dev_alloc((size_t) m_elem * (size_t) m_sweep[0].n_contrib_rows * (size_t) m_kp_cap);
             m_rbuf = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) m_kp_cap);
             m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) m_kp_cap);
             const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);

@@ -32,6 +32,7 @@ struct SweepDev {
     int n_slots = 0;
     int n_task_levels = 0;
     int max_local_rows = 0;  // largest local task (rows held in shared memory)
+    int64_t n_contrib_rows = 0;  // rows of the contribution buffer this sweep writes (forward only)
     int64_t n_stored_values = 0;
 };
 
@@ -48,7 +49,8 @@ struct ImageShape {
     int64_t n_levels[2] = {0, 0};  // reference level counts (lower, upper)
     int64_t max_local_rows[2] = {0, 0};
     int64_t exact_order = 0;  // the image was built with ScheduleOptions::exact_order (selects the *_exact kernels)
-    static constexpr int kWords = 15;
+    int64_t n_contrib_rows = 0;  // rows of the forward sweep's contribution buffer
+    static constexpr int kWords = 16;
     void to_words(int64_t *w) const;
     static ImageShape from_words(const int64_t *w);
 };
@@ -112,6 +114,7 @@ private:
     void *m_counters = nullptr; // int32[8]: [0,1] sweep tickets, [2] analysis ticket, [3] analysis max level
     void *m_tmp = nullptr;      // Float[n*k]
     void *m_rbuf = nullptr;     // Float[n*round4(k)]: residuals of the inverse super-blocks
+    void *m_cbuf = nullptr;     // Float[n_contrib_rows*round4(k)]: forward contributions of the local tasks
     void *m_scratch = nullptr;  // Float[max n_slots * 16 * k]: parked partial tiles
     int m_kp_cap = 0;           // padded RHS width the work buffers are allocated for (grow-only)
     // solve_host: device staging + two copy streams so that the H2D copy of column block c + 1, the sweeps of

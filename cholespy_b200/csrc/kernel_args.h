@@ -41,6 +41,7 @@ struct SweepArgs {
     Float *dst;           // backward: user's x
     Float *scratch;       // n_slots tiles of 16 x round4(k)
     Float *rbuf;          // (n, round4(k)) residual vector of the inverse super-blocks
+    Float *cbuf;          // (n_contrib_rows, round4(k)) forward contributions of the local tasks
     unsigned long long *trace;  // optional (debug): 8 words per task {start ns, slab ready ns, end ns, cycles spent waiting, last wait ns, blocks done ns, triangle done ns, -}
 };
 

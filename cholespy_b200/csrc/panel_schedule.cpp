@@ -70,6 +70,7 @@ ScheduleOptions schedule_options_from_env() {
     o.local_ext = std::max(0, std::min(31, geti("CHB_LOCAL_EXT", o.local_ext)));  // one loader lane per external row
     o.local_cost = std::max(1, geti("CHB_LOCAL_COST", o.local_cost));
     o.inv_panels = std::max(0, std::min(64, geti("CHB_INV_PANELS", o.inv_panels)));
+    o.contributions = geti("CHB_CONTRIBUTIONS", o.contributions ? 1 : 0) != 0;
     o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));
     o.chunk_cost = std::max(256, geti("CHB_CHUNK_COST", o.chunk_cost));
     if (const char *v = std::getenv("CHB_RELAX_ALPHA")) o.relax_alpha = std::max(1.0, std::atof(v));
@@ -189,6 +190,14 @@ struct Builder {
     std::vector<int> loc_ext;
     // inverse super-blocks: A tasks end by storing the residual instead of solving the triangle
     std::vector<int> local_root;  // root panel of the local subtree a panel belongs to, or -1
+    // forward contributions of local tasks (see REC_ADD_ROWS): per local task its external target rows (sorted) and
+    // the row of the contribution buffer its first contribution goes to
+    struct Contribution {
+        int64_t base = 0;
+        std::vector<int> rows;
+    };
+    std::vector<Contribution> contrib_of_task;
+    bool contributions() const { return !upper && !opt.exact_order && opt.contributions; }
     int64_t stat_blocks_from_local = 0, stat_rows_from_local = 0, stat_vals_from_local = 0, stat_blocks_nonlocal = 0, stat_rows_nonlocal = 0, stat_ext_rows = 0;
     bool end_store_r = false;
     std::vector<int> atask_of_panel;
@@ -439,9 +448,47 @@ struct Builder {
     }
 
     // One whole panel inside the current task.
+    // Forward sweep, fast mode: what the local tasks below contribute to panel P arrives as ready-made partial sums
+    // (one contribution row per target row and producer task, REC_ADD_ROWS) instead of one block per source panel:
+    // the products are formed by the producer while its unknowns sit in shared memory.  Removes those blocks from
+    // `blocks` and emits the additions.
+    std::vector<int> take_contributions(std::vector<int64_t> &blocks) {
+        std::vector<int> producers;
+        if (!contributions()) return producers;
+        size_t keep = 0;
+        for (int64_t b : blocks) {
+            const int src = S.b_src[b];
+            if (local_root[src] >= 0) {
+                const int t = task_of_panel[src];
+                if (producers.empty() || producers.back() != t) producers.push_back(t);  // a task's panels are consecutive
+            } else {
+                blocks[keep++] = b;
+            }
+        }
+        blocks.resize(keep);
+        return producers;
+    }
+    void emit_add_rows(int P, const std::vector<int> &producers) {
+        const int row_lo = S.c0[P], row_hi = S.c0[P + 1];
+        for (int t : producers) {
+            const Contribution &c = contrib_of_task[(size_t) t];
+            const auto first = std::lower_bound(c.rows.begin(), c.rows.end(), row_lo);
+            const auto last = std::lower_bound(c.rows.begin(), c.rows.end(), row_hi);
+            const int nt = (int) (last - first);
+            if (nt <= 0) throw std::logic_error("panel schedule: a producer without contribution rows");
+            uint32_t tmask = 0;
+            for (auto it = first; it != last; ++it) tmask |= 1u << (*it - row_lo);
+            const int64_t crow = c.base + (int64_t) (first - c.rows.begin());
+            if (crow >= (int64_t) 1 << 31) throw std::logic_error("panel schedule: contribution buffer too large");
+            w.record(REC_ADD_ROWS, (int32_t) crow, (uint32_t) nt | tmask << 16, wait_code(t), 0);
+        }
+    }
+
     void emit_panel(int P, std::vector<int64_t> &blocks) {
         order_by_readiness(blocks);
+        const std::vector<int> producers = take_contributions(blocks);
         emit_begin_rhs(P);
+        emit_add_rows(P, producers);
         for (int64_t b : blocks) emit_block(P, b);
         emit_end_final(P);
     }
@@ -449,6 +496,7 @@ struct Builder {
     // A large panel: chunk tasks + a final task.
     void emit_split_panel(int P, std::vector<int64_t> &blocks) {
         order_by_readiness(blocks);
+        const std::vector<int> producers = take_contributions(blocks);
         std::vector<size_t> cut{0};  // chunk boundaries in `blocks`
         int64_t acc = 0;
         for (size_t i = 0; i < blocks.size(); ++i) {
@@ -477,10 +525,12 @@ struct Builder {
         open_task();
         if (n_chunks == 1) {
             emit_begin_rhs(P);
+            emit_add_rows(P, producers);
         } else if (opt.exact_order) {
             emit_begin_slot(P, slot[n_chunks - 2], task[n_chunks - 2]);
         } else {
             emit_begin_rhs(P);
+            emit_add_rows(P, producers);
             for (int c = 0; c + 1 < n_chunks; ++c) emit_add_slot(slot[c], task[c]);
         }
         for (size_t i = cut[n_chunks - 1]; i < cut[n_chunks]; ++i) emit_block(P, blocks[i]);
@@ -512,38 +562,54 @@ struct Builder {
             }
         }
         (void) lo, (void) hi;
+        // forward contributions: one more sparse row per external target row r, local row n_int + e, accumulated from
+        // zero: -(sum over the task's columns c of L[r, c] x[c]); the target panel adds it (REC_ADD_ROWS)
+        const int n_out = contributions() ? (int) loc_ext.size() : 0;
+        if (n_out > 0) {
+            rows.resize((size_t) (n_int + n_out));
+            diag.resize((size_t) (n_int + n_out), 1.0);
+            for (int j = 0; j < n_int; ++j) {
+                const int c = c_lo + j;
+                for (int e = L.colptr[c + 1] - 1; e > L.colptr[c] && L.rowidx[e] >= c_lo + n_int; --e)
+                    rows[(size_t) local_index(L.rowidx[e])].push_back(Entry{j, L.vals[(size_t) e]});
+            }
+        }
+        const int n_rows_total = n_int + n_out;
         const size_t es = (size_t) img.elem;
         auto row_bytes = [&](int j) {
             const size_t n4 = (rows[j].size() + 3) / 4;
             return 16 + round16(4 * n4) + 4 * n4 * es;
         };
+        std::vector<int> sequence((size_t) n_rows_total);  // rows in processing order
+        for (int q = 0; q < n_rows_total; ++q) sequence[(size_t) q] = upper ? n_int - 1 - q : q;
         int j = 0;
-        while (j < n_int) {
+        while (j < n_rows_total) {
             // as many rows as fit one page (a record never straddles a page)
             size_t bytes = 0;
             int cnt = 0;
-            while (j + cnt < n_int && 16 + bytes + row_bytes(upper ? n_int - 1 - (j + cnt) : j + cnt) <= (size_t) img.page_bytes) {
-                bytes += row_bytes(upper ? n_int - 1 - (j + cnt) : j + cnt);
+            while (j + cnt < n_rows_total && 16 + bytes + row_bytes(sequence[(size_t) (j + cnt)]) <= (size_t) img.page_bytes) {
+                bytes += row_bytes(sequence[(size_t) (j + cnt)]);
                 cnt += 1;
             }
             if (cnt == 0) throw std::logic_error("panel schedule: a local row does not fit a page");
             const size_t off = w.record(REC_LOCAL_ROWS, cnt, opt.exact_order ? 0u : 1u, 0, bytes);
             size_t at = off;
             for (int q = 0; q < cnt; ++q) {
-                const int r = upper ? n_int - 1 - (j + q) : j + q;
+                const int r = sequence[(size_t) (j + q)];
+                const bool contribution = r >= n_int;  // accumulated from zero, no pivot
                 const std::vector<Entry> &ent = rows[(size_t) r];
                 const size_t n4 = (ent.size() + 3) / 4;
                 if (n4 > 255) throw std::logic_error("panel schedule: local row too long");
-                w.put_int(at, 0, (int32_t) ((uint32_t) r | (uint32_t) n4 << 8));
+                w.put_int(at, 0, (int32_t) ((uint32_t) r | (uint32_t) n4 << 8 | (contribution ? 1u << 16 : 0u)));
                 // the pivot at byte 8: reciprocal in fast mode (multiply), the diagonal itself in exact-order mode (IEEE divide)
-                w.put_value(at + 8, 0, opt.exact_order ? diag[(size_t) r] : 1.0 / diag[(size_t) r]);
+                w.put_value(at + 8, 0, contribution ? 1.0 : opt.exact_order ? diag[(size_t) r] : 1.0 / diag[(size_t) r]);
                 uint8_t idx[1024];
-                for (size_t i = 0; i < 4 * n4; ++i) idx[i] = (uint8_t) (i < ent.size() ? ent[i].idx : r);
+                for (size_t i = 0; i < 4 * n4; ++i) idx[i] = (uint8_t) (i < ent.size() ? ent[i].idx : contribution ? 0 : r);
                 w.put_bytes(at + 16, idx, 4 * n4);
                 const size_t voff = at + 16 + round16(4 * n4);
                 for (size_t i = 0; i < ent.size(); ++i) w.put_value(voff, i, ent[i].v);
                 at = voff + 4 * n4 * es;
-                img.n_values += (int64_t) ent.size() + 1;
+                img.n_values += (int64_t) ent.size() + (contribution ? 0 : 1);
                 img.n_stored_values += (int64_t) (4 * n4) + 1;
             }
             j += cnt;
@@ -558,17 +624,26 @@ struct Builder {
         loc_n_int = S.c0[hi + 1] - loc_lo;
         loc_ext.clear();
         std::vector<uint32_t> waits;
-        if (upper) {
-            // every row a subtree reads from outside lies in the below-panel row list of its root; a task may hold
+        if (upper || contributions()) {
+            // every row a subtree reads from outside (backward) or contributes to (forward) lies in the below-panel row list of its root; a task may hold
             // several adjacent subtrees (a forest): the union over their roots
             for (int P = lo; P <= hi; ++P)
                 if (local_root[P] == P) loc_ext.insert(loc_ext.end(), S.rows.begin() + S.rlo[P], S.rows.begin() + S.rlo[P] + S.m[P]);
             std::sort(loc_ext.begin(), loc_ext.end());
             loc_ext.erase(std::unique(loc_ext.begin(), loc_ext.end()), loc_ext.end());
-            for (int r : loc_ext) {
-                const uint32_t code = wait_code(task_of_panel[S.panel_of_row[r]]);
-                if (code && std::find(waits.begin(), waits.end(), code) == waits.end()) waits.push_back(code);
-            }
+            if (upper)
+                for (int r : loc_ext) {
+                    const uint32_t code = wait_code(task_of_panel[S.panel_of_row[r]]);
+                    if (code && std::find(waits.begin(), waits.end(), code) == waits.end()) waits.push_back(code);
+                }
+        }
+        int64_t contrib_base = 0;
+        if (contributions()) {
+            if ((size_t) cur >= contrib_of_task.size()) contrib_of_task.resize((size_t) cur + 1);
+            contrib_base = img.n_contrib_rows;
+            contrib_of_task[(size_t) cur].base = contrib_base;
+            contrib_of_task[(size_t) cur].rows = loc_ext;
+            img.n_contrib_rows += (int64_t) loc_ext.size();
         }
         const int n_ext = (int) loc_ext.size(), n_wait = (int) waits.size();
         stat_ext_rows += n_ext;
@@ -588,7 +663,9 @@ struct Builder {
         emit_local_rows(lo, hi);
         for (int P = lo; P <= hi; ++P) task_of_panel[P] = cur;
         {
-            const size_t off = w.record(REC_LOCAL_STORE, loc_lo, (uint32_t) loc_n_int, 0, upper ? 4 * pad4(loc_n_int) : 0);
+            if (contrib_base >= (int64_t) 1 << 31) throw std::logic_error("panel schedule: contribution buffer too large");
+            const size_t off = w.record(REC_LOCAL_STORE, loc_lo, (uint32_t) loc_n_int | (upper ? 0u : (uint32_t) n_ext << 16),
+                                        (uint32_t) contrib_base, upper ? 4 * pad4(loc_n_int) : 0);
             if (upper)
                 for (int i = 0; i < loc_n_int; ++i) w.put_int(off, (size_t) i, L.perm[loc_lo + i]);
         }

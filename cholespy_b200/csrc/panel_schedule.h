@@ -81,6 +81,11 @@ enum RecordType : uint32_t {
                          // as sparse rows, in sweep order; per row: 16-byte header {u32 local_row | n4 << 8, pad, pivot at
                          // byte 8}, 4 n4 local source indices (u8, padded to 16 bytes), 4 n4 values:
                          // local[row] = (local[row] - sum values[i] * local[idx[i]]) * or / pivot
+    REC_ADD_ROWS = 15,   // a = first row of the contribution buffer, b = nt | tmask << 16, c = wait + 1: tile[t] += contribution
+                         // row, for the nt targets of tmask in ascending order.  Forward sweep, fast mode: what a local task
+                         // contributes to this panel, formed by the producer (its LOCAL_ROWS rows with bit 16 of the meta
+                         // word set: accumulated from zero into local row n_int + e; LOCAL_STORE, c = first contribution
+                         // row, b = n_int | n_ext << 16, writes them out)
     REC_END_STORE = 13,  // a = row0, b = w, c = destination: 0 = the work vector (payload backward: perm[16]; publishes the
                          // panel), 1 = the residual vector r of an inverse super-block.  No triangle.
     REC_SRC_R_FLAG = 0x80, // on a BLOCK record: the source rows are rows of the residual vector r, not of the work vector
@@ -100,6 +105,7 @@ struct ScheduleOptions {
     int chunk_cost = 2048;    // values per chunk task
     double relax_alpha = 1.5; // relaxed panels: stored values <= alpha * non-zeros + beta (1.0 / 0: no fill)
     double relax_beta = 32.0;
+    bool contributions = true;// forward sweep, fast mode: local tasks hand their parents ready-made partial sums (REC_ADD_ROWS)
     int inv_panels = 32;      // consecutive panels of one supernode whose diagonal block is applied as an explicit
                               // inverse (fast mode only; < 2: off).  See "inverse super-blocks" below.
     bool exact_order = false; // true: chunks are CHAINED (reference summation order kept bit for bit)
@@ -143,6 +149,7 @@ struct SweepImage {
     std::vector<TaskDesc> tasks;
     std::vector<int32_t> order;      // ticket -> task id, sorted by level (dependencies first)
     int n_slots = 0;                 // scratch tiles (kPanelWidth x n_rhs elements each)
+    int64_t n_contrib_rows = 0;      // rows of the contribution buffer (forward sweep)
     int max_local_rows = 0;          // largest n_int + n_ext over the local tasks (sizes the kernels' shared memory)
     int n_levels = 0;
     int64_t n_values = 0;            // factor values referenced (== nnz(L))

@@ -62,7 +62,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 enum : uint32_t { REC_NOP = 0, REC_BEGIN_RHS, REC_BEGIN_ZERO, REC_BEGIN_SLOT, REC_ADD_SLOT, REC_BLOCK_D4, REC_BLOCK_D1,
                   REC_BLOCK_TM, REC_END_FINAL, REC_END_SLOT, REC_END_DENSE, REC_LOCAL_LOAD, REC_LOCAL_STORE,
-                  REC_END_STORE, REC_LOCAL_ROWS, REC_LOCAL_FLAG = 0x40, REC_SRC_R_FLAG = 0x80 };
+                  REC_END_STORE, REC_LOCAL_ROWS, REC_ADD_ROWS, REC_LOCAL_FLAG = 0x40, REC_SRC_R_FLAG = 0x80 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -266,6 +266,7 @@ __device__ __forceinline__ int staged_rows(const uint4 &h) {
     const uint32_t type = h.x & 0x7f;  // records inside local tasks carry REC_LOCAL_FLAG and never match
     if (type == REC_BLOCK_D4) return __popc(h.z & 0xffff);
     if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) return W;
+    if (type == REC_ADD_ROWS) return (int) (h.z & 0xffff);
     if (type == REC_BEGIN_RHS) return (int) h.z;
     if (type == REC_LOCAL_LOAD) return (int) (h.z & 0xffff) + (int) (h.z >> 16);
     return 0;
@@ -534,6 +535,8 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                         }
                     } else if (type == REC_BEGIN_SLOT || type == REC_ADD_SLOT) {
                         if (lane == 0) from = a.scratch + (size_t) (h.z >> 8) * W * kp, n_copy = W;
+                    } else if (!UPPER && type == REC_ADD_ROWS) {
+                        if (lane == 0) from = a.cbuf + (size_t) h.y * kp, n_copy = nr;
                     } else if (type == REC_BEGIN_RHS) {
                         if (UPPER) {
                             if (lane == 0) from = a.tmp + (size_t) (int) h.y * kp, n_copy = nr;
@@ -679,7 +682,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         const unsigned char *idx = q + 16;
                         const F *val = reinterpret_cast<const F *>(q + 16 + ((4 * n4 + 15) & ~15));
                         F *dst = lrow + (size_t) (meta & 0xff) * kp;
-                        F acc = *dst;
+                        F acc = (meta >> 16 & 1) ? F(0) : *dst;  // bit 16: a contribution row, accumulated from zero
                         for (int g = 0; g < n4; ++g) {
                             const uint32_t i4 = *reinterpret_cast<const uint32_t *>(idx + 4 * g);
                             const Vec4<F> vv = Vec4<F>::load(val + 4 * g);
@@ -690,6 +693,19 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         if (active) *dst = acc;
                         q = reinterpret_cast<const unsigned char *>(val + 4 * n4);
                     }
+                } else if (!UPPER && type == REC_ADD_ROWS) {
+                    // partial sums formed by the local tasks below: tile[t] += row, targets of tmask in ascending order
+                    const int nt = (int) (h.z & 0xffff);
+                    const uint32_t tmask = h.z >> 16;
+                    const F *row = &ring_at(acquire_rows(nt), 0);
+#pragma unroll
+                    for (int t = 0; t < W; ++t) {
+                        if (tmask >> t & 1) {
+                            T[t] += *row;
+                            row += kp;
+                        }
+                    }
+                    release_rows(nt);
                 } else if (type == REC_BEGIN_RHS) {
                     row0 = (int) h.y;
                     w = (int) h.z;
@@ -721,13 +737,18 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                     lrows = (int) (h.z & 0xffff) + (int) (h.z >> 16);
                     lbase = acquire_rows(lrows);   // held until LOCAL_STORE
                 } else if (type == REC_LOCAL_STORE) {
-                    const int lo = (int) h.y, n_int = (int) h.z;
+                    const int lo = (int) h.y, n_int = (int) (h.z & 0xffff), n_out = (int) (h.z >> 16);
                     const int *perm = reinterpret_cast<const int *>(pay);
                     if (active) {
                         for (int i = 0; i < n_int; ++i) {
                             const F v = ring_at(lbase, i);
                             __stcg(a.tmp + (size_t) (lo + i) * kp + col, v);
                             if (UPPER) a.dst[(size_t) perm[i] * k + col] = v;
+                        }
+                        // forward: the task's contributions to its ancestors' rows (local rows n_int ...) -> contribution buffer
+                        if (!UPPER) {
+                            F *out = a.cbuf + (size_t) h.w * kp + col;
+                            for (int e = 0; e < n_out; ++e) __stcg(out + (size_t) e * kp, ring_at(lbase, n_int + e));
                         }
                     }
                     release_rows(lrows);

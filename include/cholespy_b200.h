@@ -106,7 +106,7 @@ void chb_factor_destroy(chb_factor *f);
  * orders): build the solver on one GPU, read its shape, create empty replicas of the same shape on
  * the others, and broadcast each image buffer (NCCL) from the source into the replica.  New; the
  * reference is single-GPU.  shape = CHB_IMAGE_SHAPE_WORDS int64 words. */
-#define CHB_IMAGE_SHAPE_WORDS 15
+#define CHB_IMAGE_SHAPE_WORDS 16
 int chb_solver_image_shape(const chb_solver *s, int64_t *shape, int cap);
 int chb_solver_create_replica(chb_solver **out, int dtype, const int64_t *shape, int n_words, int device);
 int chb_solver_image_count(const chb_solver *s);

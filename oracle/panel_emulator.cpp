@@ -26,7 +26,7 @@ inline double fnma(double a, double b, double c) { return __builtin_fma(-a, b, c
 inline int span16(uint32_t m) { return m ? 32 - __builtin_clz(m) : 0; }
 
 enum { NOP = 0, BEGIN_RHS, BEGIN_ZERO, BEGIN_SLOT, ADD_SLOT, BLOCK_D4, BLOCK_D1, BLOCK_TM, END_FINAL, END_SLOT, END_DENSE,
-       LOCAL_LOAD, LOCAL_STORE, END_STORE, LOCAL_ROWS, LOCAL_FLAG = 0x40, SRC_R_FLAG = 0x80 };
+       LOCAL_LOAD, LOCAL_STORE, END_STORE, LOCAL_ROWS, ADD_ROWS, LOCAL_FLAG = 0x40, SRC_R_FLAG = 0x80 };
 
 // returns 0, or a negative error code
 template <typename F>
@@ -34,6 +34,7 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
         const F *b, F *x, F *scratch) {
     std::vector<uint8_t> done((size_t) n_tasks, 0);
     std::vector<F> acc((size_t) W * k);
+    std::vector<F> cbuf;  // contribution buffer of the forward sweep (grown on demand)
     std::vector<F> rbuf;  // residual vector of the inverse super-blocks (grown on demand)
     std::vector<F> loc;  // rows of the local task being executed: [n_int unknowns | n_ext external rows] x k
     int loc_rows = 0;
@@ -73,7 +74,7 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                     loc_rows = n_int + n_ext;
                     loc.assign((size_t) loc_rows * k, F(0));
                     if (!upper) {
-                        if (n_ext || n_wait) return -7;
+                        if (n_wait) return -7;  // n_ext rows (zero here) receive the task's contributions
                         for (int i = 0; i < n_int; ++i)
                             for (int c = 0; c < k; ++c) loc[(size_t) i * k + c] = b[(size_t) list[i] * k + c];
                     } else {
@@ -94,13 +95,14 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                         uint32_t meta;
                         std::memcpy(&meta, q, 4);
                         const int row = (int) (meta & 0xff), n4 = (int) (meta >> 8 & 0xff);
+                        const bool from_zero = (meta >> 16 & 1) != 0;
                         F piv;
                         std::memcpy(&piv, q + 8, sizeof(F));
                         const uint8_t *idx = q + 16;
                         const F *val = (const F *) (q + 16 + ((4 * n4 + 15) & ~15));
                         if (row >= loc_rows) return -7;
                         for (int c = 0; c < k; ++c) {
-                            F acc = loc[(size_t) row * k + c];
+                            F acc = from_zero ? F(0) : loc[(size_t) row * k + c];
                             for (int e = 0; e < 4 * n4; ++e) {
                                 if ((int) idx[e] >= loc_rows) return -7;
                                 acc = fnma(val[e], loc[(size_t) idx[e] * k + c], acc);
@@ -110,8 +112,28 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                         q = (const uint8_t *) (val + 4 * n4);
                     }
                 } break;
+                case ADD_ROWS: {
+                    if (!waited(h[3])) return -4;
+                    const size_t first = (size_t) h[1];
+                    const int nt = (int) (h[2] & 0xffff);
+                    const uint32_t tmask = h[2] >> 16;
+                    if ((first + nt) * k > cbuf.size()) return -7;
+                    int r = 0;
+                    for (int t = 0; t < W; ++t) {
+                        if (!(tmask >> t & 1)) continue;
+                        for (int c = 0; c < k; ++c) acc[(size_t) t * k + c] += cbuf[(first + r) * k + c];
+                        ++r;
+                    }
+                    if (r != nt) return -5;
+                } break;
                 case LOCAL_STORE: {
-                    const int lo = (int) h[1], n_int = (int) h[2];
+                    const int lo = (int) h[1], n_int = (int) (h[2] & 0xffff), n_out = (int) (h[2] >> 16);
+                    if (n_out) {
+                        const size_t first = (size_t) h[3];
+                        if (cbuf.size() < (first + n_out) * k) cbuf.resize((first + n_out) * k, F(0));
+                        for (int e = 0; e < n_out; ++e)
+                            for (int c = 0; c < k; ++c) cbuf[(first + e) * k + c] = loc[(size_t) (n_int + e) * k + c];
+                    }
                     const int32_t *perm = (const int32_t *) pay;
                     for (int i = 0; i < n_int; ++i)
                         for (int c = 0; c < k; ++c) {
