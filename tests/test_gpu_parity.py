@@ -307,3 +307,21 @@ def test_degenerate_systems():
                 x = _gpu_solve(s, b)
                 x_ref = spsolve(A, b.astype(np.float64)).reshape(n, k)
                 assert max_rel_err(x, x_ref) < (2e-6 if dtype == np.float32 else 1e-13), (n, offdiag, k)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_patterns_on_the_gpu(seed, oracle_mod, native_lib):
+    """Irregular (non-mesh) SPD patterns through the GPU path: both the fast and the exact-order kernels."""
+    from test_schedule import _random_spd
+    rng = np.random.default_rng(200 + seed)
+    n = int(rng.integers(50, 3000))
+    A = _random_spd(n, float(rng.uniform(0.001, 0.01)), seed)
+    perm, cp, ri, v = factorize(native_lib, n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, "CSC")
+    for dtype in (np.float32, np.float64):
+        Solver = CholeskySolverF if dtype == np.float32 else CholeskySolverD
+        s = Solver(n, torch.tensor(A.indptr.astype(np.int32), device="cuda"), torch.tensor(A.indices.astype(np.int32), device="cuda"),
+                   torch.tensor(A.data, device="cuda"), MatrixType.CSC)
+        for k in (1, 6, 128):
+            b = rng.random((n, k)).astype(dtype)
+            x = _gpu_solve(s, b)
+            assert max_rel_err(x, oracle_mod.solve(cp, ri, v, perm, b)) < TOL[np.dtype(dtype)], (seed, n, k)

@@ -35,3 +35,34 @@ def test_fast_schedule_within_tolerance(name, dtype, oracle_mod, native_lib):
     x, fwd, bwd = oracle_mod.schedule_solve(native_lib, cp, ri, v, perm, b, exact_order=0)
     assert fwd["n_values"] == len(ri) and bwd["n_values"] == len(ri)
     assert max_rel_err(x, x_ref) < TOL[np.dtype(dtype)], name
+
+
+def _random_spd(n, density, seed):
+    """A = B B' + n I with a random sparse B plus a band (irregular elimination trees: chains, stars, wide fronts)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    B = sp.random(n, n, density=density, random_state=rng, data_rvs=rng.standard_normal, format="csr")
+    band = sp.diags([rng.standard_normal(n - 1), rng.standard_normal(max(n - 7, 0))], [-1, -7], shape=(n, n))
+    B = (B + band).tocsr()
+    A = (B @ B.T + float(n) * sp.identity(n)).tocsc()
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_patterns_exact_and_fast(seed, oracle_mod, native_lib):
+    """Irregular sparsity patterns (not meshes): the exact-order schedule stays bit-identical to the oracle and the
+    fast schedule (relaxed panels, sparse-row local tasks, contributions, inverse super-blocks) stays within tolerance."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(20, 500))
+    A = _random_spd(n, float(rng.uniform(0.002, 0.03)), seed)
+    perm, cp, ri, v = factorize(native_lib, n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, "CSC")
+    for dtype in (np.float32, np.float64):
+        b = rng.random((n, int(rng.integers(1, 9)))).astype(dtype)
+        x_ref = oracle_mod.solve(cp, ri, v, perm, b)
+        x_exact, fwd, bwd = oracle_mod.schedule_solve(native_lib, cp, ri, v, perm, b, exact_order=1)
+        assert np.array_equal(x_exact, x_ref.astype(dtype)), (seed, n)
+        assert fwd["n_values"] == len(ri) and bwd["n_values"] == len(ri)
+        x_fast, fwd, bwd = oracle_mod.schedule_solve(native_lib, cp, ri, v, perm, b, exact_order=0)
+        assert fwd["n_values"] == len(ri) and bwd["n_values"] == len(ri)
+        assert max_rel_err(x_fast, x_ref) < TOL[np.dtype(dtype)], (seed, n)
