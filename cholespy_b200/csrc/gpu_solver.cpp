@@ -79,13 +79,15 @@ int padded_rhs(int k) { return (k + 3) & ~3; }  // row stride of the work vector
 int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 RHS columns (+ 1 loader warp).  Wider lanes
 // (2 or 4 columns per lane, fewer warps) were measured slower on ico8 and ico9 at 64..128 RHS: tasks are latency-bound.
 
-// Rows of the shared-memory row ring: room for the largest local task plus two full blocks, about 36 KB
+// Rows of the shared-memory row ring: room for the largest local task plus one full block, at least about 36 KB
 // (four CTAs per SM at 128 single-precision right-hand sides; measured: occupancy beats ring depth).
 int sweep_ring_rows(int elem, int k, int local_rows) {
     const int row_bytes = padded_rhs(k) * elem;
     int budget_kb = 36;
     if (const char *v = std::getenv("CHB_RING_KB")) budget_kb = std::max(1, std::atoi(v));
-    return std::max(local_rows + 32, std::min(256, (budget_kb << 10) / row_bytes));
+    int slack = 16;  // rows beyond the largest local task: one full block next to it (measured on cfg4: 16 beats 32, one more CTA per SM)
+    if (const char *v = std::getenv("CHB_RING_SLACK")) slack = std::max(16, std::atoi(v));
+    return std::max(local_rows + slack, std::min(256, (budget_kb << 10) / row_bytes));
 }
 
 // Dynamic shared memory of one sweep CTA (sweep.cuh: struct Smem).
