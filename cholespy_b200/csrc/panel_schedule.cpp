@@ -697,8 +697,8 @@ struct Builder {
             sub_count[q] += sub_count[P];
             first[q] = std::min(first[q], first[P]);
         }
-        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 32 : 48);
-        const int max_ext = opt.local_ext > 0 ? opt.local_ext : 31;  // <= 31: one loader lane per external row
+        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 32 : 36);
+        const int max_ext = opt.local_ext > 0 ? opt.local_ext : (img.elem == 8 ? 31 : 24);  // <= 31: one loader lane per external row
         std::vector<int> root_of(np, -1);  // root of the local task a panel belongs to, or -1
         for (int P = np - 1; P >= 0; --P) {
             if (root_of[P] >= 0) continue;  // already inside a local subtree

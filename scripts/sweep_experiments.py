@@ -30,7 +30,11 @@ def main():
     perm, cp, ri, v = bench.get_factor(name, p)
     lib = _capi.load()
     A = problems.to_scipy_csc(p)
+    touched = set()
     for build in builds:
+        for key in touched:  # a build must not inherit the previous build's settings
+            os.environ.pop(key, None)
+        touched = {kv.split("=")[0] for kv in filter(None, build.split("+"))}
         for kv in filter(None, build.split("+")):
             key, val = kv.split("=")
             os.environ[key] = val
