@@ -185,7 +185,6 @@ struct Builder {
     int cur = -1;
     uint32_t cur_level = 0;
     // local task being emitted (see REC_LOCAL_LOAD): unknowns [loc_lo, loc_lo + loc_n_int), then the external rows
-    bool local = false;
     int loc_lo = 0, loc_n_int = 0;
     std::vector<int> loc_ext;
     // inverse super-blocks: A tasks end by storing the residual instead of solving the triangle
@@ -291,7 +290,6 @@ struct Builder {
     }
 
     // -- records --------------------------------------------------------------------------------
-    uint32_t flag() const { return local ? (uint32_t) REC_LOCAL_FLAG : 0u; }
     int local_index(int row) const {
         if (row >= loc_lo && row < loc_lo + loc_n_int) return row - loc_lo;
         const auto it = std::lower_bound(loc_ext.begin(), loc_ext.end(), row);
@@ -301,9 +299,7 @@ struct Builder {
 
     void emit_begin_rhs(int P) {
         const int wd = S.width(P), row0 = S.c0[P];
-        if (local) {
-            w.record(REC_BEGIN_RHS | REC_LOCAL_FLAG, row0 - loc_lo, (uint32_t) wd, 0, 0);
-        } else if (upper) {
+        if (upper) {
             w.record(REC_BEGIN_RHS, row0, (uint32_t) wd, 0, 0);
         } else {
             const size_t off = w.record(REC_BEGIN_RHS, row0, (uint32_t) wd, 0, 4 * kPanelWidth);
@@ -325,18 +321,6 @@ struct Builder {
         img.n_blocks += 1;
         double buf[kPanelWidth][kPanelWidth];  // [row of the block][column of p]
         img.n_values += gather_block(p, q0, nr, buf);
-        // local tasks: 16 bytes of local source-row indices (sweep order) precede the values
-        const size_t idx_bytes = local ? 16 : 0;
-        auto put_sources = [&](size_t off, int first_row, uint32_t mask, bool descending) {
-            if (!local) return;
-            uint8_t idx[16] = {0};
-            int r = 0;
-            for (int bit = 0; bit < kPanelWidth; ++bit) {
-                const int sbit = descending ? kPanelWidth - 1 - bit : bit;
-                if (mask >> sbit & 1) idx[r++] = (uint8_t) local_index(first_row + sbit);
-            }
-            w.put_bytes(off, idx, 16);
-        };
         // One layout for every block ("grouped source-major"): per source, in sweep order, the values of the
         // 4-target GROUPS that contain at least one target (zero-filled inside a group).  Explicit zeros
         // are bit-neutral under fused multiply-subtract.
@@ -347,15 +331,12 @@ struct Builder {
         int group_rank[4], ng = 0;
         for (int g = 0; g < 4; ++g) group_rank[g] = (tmask >> (4 * g) & 0xf) ? ng++ : -1;
         const int stride = 4 * ng;
-        const uint32_t wait = local ? 0u : wait_code(task_of_panel[upper ? t : p]);
+        const uint32_t wait = wait_code(task_of_panel[upper ? t : p]);
         (void) P;
-        if (!upper && !local && !local_root.empty() && local_root[p] >= 0) stat_blocks_from_local += 1, stat_rows_from_local += ns, stat_vals_from_local += (int64_t) ns * popc16(tmask);
-        if (!upper && !local) stat_blocks_nonlocal += 1, stat_rows_nonlocal += ns;
-        const size_t off0 = w.record(REC_BLOCK_D4 | flag(), S.c0[upper ? t : p], smask | tmask << 16, wait,
-                                     idx_bytes + es * (size_t) ns * (size_t) stride);
+        if (!upper && !local_root.empty() && local_root[p] >= 0) stat_blocks_from_local += 1, stat_rows_from_local += ns, stat_vals_from_local += (int64_t) ns * popc16(tmask);
+        if (!upper) stat_blocks_nonlocal += 1, stat_rows_nonlocal += ns;
+        const size_t off = w.record(REC_BLOCK_D4, S.c0[upper ? t : p], smask | tmask << 16, wait, es * (size_t) ns * (size_t) stride);
         // backward: sources visited in DESCENDING row order (the reference walks a row of L' from its end backwards)
-        put_sources(off0, S.c0[upper ? t : p], smask, upper);
-        const size_t off = off0 + idx_bytes;
         for (int r = 0; r < ns; ++r) {
             int q = 0;  // rank of the target among the block's rows (forward)
             for (int tt = 0; tt < kPanelWidth; ++tt) {
@@ -375,9 +356,8 @@ struct Builder {
         const int wd = S.width(P), row0 = S.c0[P];
         const size_t es = (size_t) img.elem;
         const int wp = wd == 1 ? 1 : (wd + 3) & ~3;
-        const size_t head = upper && !local ? 4 * kPanelWidth : 0;
-        const size_t off = w.record(REC_END_DENSE | flag(), local ? row0 - loc_lo : row0, (uint32_t) wd, 0,
-                                    head + es * (size_t) (wp * wp));
+        const size_t head = upper ? 4 * kPanelWidth : 0;
+        const size_t off = w.record(REC_END_DENSE, row0, (uint32_t) wd, 0, head + es * (size_t) (wp * wp));
         if (head)
             for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
         int present = 0;
@@ -427,8 +407,8 @@ struct Builder {
         const int wd = S.width(P), row0 = S.c0[P];
         const size_t es = (size_t) img.elem;
         const size_t tri_bytes = round16(es * (size_t) (wd * (wd + 1) / 2));
-        const size_t head = upper && !local ? 4 * kPanelWidth : 0;  // backward: perm[16] first (x is scattered through it)
-        const size_t off = w.record(REC_END_FINAL | flag(), local ? row0 - loc_lo : row0, (uint32_t) wd, 0, head + tri_bytes);
+        const size_t head = upper ? 4 * kPanelWidth : 0;  // backward: perm[16] first (x is scattered through it)
+        const size_t off = w.record(REC_END_FINAL, row0, (uint32_t) wd, 0, head + tri_bytes);
         if (head)
             for (int i = 0; i < wd; ++i) w.put_int(off, (size_t) i, L.perm[row0 + i]);
         size_t idx = 0;
@@ -619,7 +599,6 @@ struct Builder {
     // One LOCAL task: the complete subtree of panels [lo, hi] (hi = its root), solved in shared memory.
     void emit_local_task(int lo, int hi, std::vector<int64_t> &blocks) {
         open_task();
-        local = true;
         loc_lo = S.c0[lo];
         loc_n_int = S.c0[hi + 1] - loc_lo;
         loc_ext.clear();
@@ -669,7 +648,6 @@ struct Builder {
             if (upper)
                 for (int i = 0; i < loc_n_int; ++i) w.put_int(off, (size_t) i, L.perm[loc_lo + i]);
         }
-        local = false;
         close_task();
     }
 

@@ -89,11 +89,7 @@ enum RecordType : uint32_t {
     REC_END_STORE = 13,  // a = row0, b = w, c = destination: 0 = the work vector (payload backward: perm[16]; publishes the
                          // panel), 1 = the residual vector r of an inverse super-block.  No triangle.
     REC_SRC_R_FLAG = 0x80, // on a BLOCK record: the source rows are rows of the residual vector r, not of the work vector
-    // Inside a local task the BEGIN_RHS / BLOCK_* / END_FINAL / END_DENSE records carry REC_LOCAL_FLAG:
-    //   BEGIN_RHS: a = local index of the panel's first row, no payload (tile = local rows)
-    //   BLOCK_*:   a unused, c = 0; payload starts with 16 bytes = local index of each source row in
-    //              sweep order, then the values as usual
-    //   END_*:     a = local index of the panel's first row; no perm payload; the tile goes back to local rows
+    // (retired: local tasks used to carry panel records marked with this flag; they are sparse rows now, REC_LOCAL_ROWS)
     REC_LOCAL_FLAG = 0x40,
 };
 
