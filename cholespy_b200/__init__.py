@@ -188,6 +188,11 @@ class _CholeskySolver:
         else:
             if cpu_solver:
                 raise ValueError("Input device is CUDA but the solver was initialized for CPU.")
+            # (new, the reference is single-device: src/cuda_driver.cpp:124) foreign pointers would fault the
+            # solver's context, which it shares with the caller's framework
+            for a in (a_b, a_x):
+                if a.device is not None and a.device != self._device:
+                    raise ValueError("x and b should be on the solver's device (cuda:%d)." % self._device)
             _capi.check(lib.chb_solver_solve_cuda(self._handle, n_rhs, a_b.ptr, a_x.ptr))
         return None
 
@@ -202,12 +207,17 @@ class _CholeskySolver:
         _capi.check(_capi.load().chb_solver_solve_host(self._handle, n_rhs, a_b.ptr, a_x.ptr))
 
     def info(self):
-        out = (ctypes.c_int64 * 18)()
-        m = _capi.load().chb_solver_info(self._handle, out, 18)
+        out = (ctypes.c_int64 * 21)()
+        m = _capi.load().chb_solver_info(self._handle, out, 21)
         keys = ("n", "nnz_l", "n_levels_lower", "n_levels_upper", "dtype", "device", "grid", "launches_per_solve",
                 "fwd_tasks", "fwd_slab_bytes", "fwd_slots", "fwd_task_levels", "fwd_stored_values",
-                "bwd_tasks", "bwd_slab_bytes", "bwd_slots", "bwd_task_levels", "bwd_stored_values")
+                "bwd_tasks", "bwd_slab_bytes", "bwd_slots", "bwd_task_levels", "bwd_stored_values",
+                "front_image", "update_rows", "compute_warps")
         return dict(zip(keys[:m], list(out)[:m]))
+
+    def check_error(self):
+        """Synchronises the device and raises RuntimeError if the sweep kernels' watchdog fired."""
+        _capi.check(_capi.load().chb_solver_check_error(self._handle))
 
     def analysis(self, lower=True):
         """(level_of_row, order): the GPU level-set analysis products (int32 numpy arrays)."""

@@ -8,7 +8,7 @@ _LIB_PATH = os.path.join(_LIB_DIR, "libcholespy_b200.so")
 OK, ERR_INVALID, ERR_RUNTIME = 0, 1, 2
 F32, F64 = 0, 1
 DEVICE_CPU = -1
-IMAGE_SHAPE_WORDS = 16
+IMAGE_SHAPE_WORDS = 24
 
 _lib = None
 
@@ -35,6 +35,7 @@ _SIGNATURES = {
     "chb_solver_solve_cuda": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
     "chb_solver_solve_host": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
     "chb_solver_solve_cpu": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
+    "chb_solver_check_error": (ctypes.c_int, [c_vp]),
     "chb_solver_is_cpu": (ctypes.c_int, [c_vp]),
     "chb_solver_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "chb_solver_get_analysis": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
@@ -53,6 +54,11 @@ _SIGNATURES = {
     "chb_schedule_sweep": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                                           ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "chb_schedule_destroy": (None, [c_vp]),
+    "chb_front_schedule_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_vp, c_vp,
+                                                 c_vp, c_vp]),
+    "chb_front_schedule_sweep": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                                ctypes.POINTER(c_vp), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "chb_front_schedule_destroy": (None, [c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

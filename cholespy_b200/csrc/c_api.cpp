@@ -9,6 +9,7 @@
 
 #include "cholesky_solver.h"
 #include "factor_host.h"
+#include "front_schedule.h"
 #include "gpu_solver.h"
 #include "panel_schedule.h"
 
@@ -30,6 +31,11 @@ struct chb_factor {
 struct chb_schedule {
     chb::PanelStructure structure;
     chb::SweepImage sweep[2];  // [0] forward (lower), [1] backward (upper)
+};
+
+struct chb_front_schedule {
+    chb::FrontStructure structure;
+    chb::FrontImage sweep[2];  // [0] forward (lower), [1] backward (upper)
 };
 
 namespace {
@@ -216,6 +222,17 @@ CHB_API int chb_solver_solve_cpu(chb_solver *s, int n_rhs, const void *b, void *
     });
 }
 
+CHB_API int chb_solver_check_error(chb_solver *s) {
+    return guarded([&] {
+        chb::GpuSolver *g = s->gpu();
+        if (!g) return;
+        const int word = g->device_error();
+        if (word != 0)
+            throw std::runtime_error("sweep watchdog: a task dependency never arrived (code " + std::to_string(word) +
+                                     "); the results of the last solves are invalid");
+    });
+}
+
 CHB_API int chb_solver_is_cpu(const chb_solver *s) { return s->is_cpu() ? 1 : 0; }
 
 CHB_API int chb_solver_info(const chb_solver *s, int64_t *out, int cap) {
@@ -225,7 +242,8 @@ CHB_API int chb_solver_info(const chb_solver *s, int64_t *out, int cap) {
     const int64_t v[] = {g->n(), g->nnz(), g->triangle(true).n_levels, g->triangle(false).n_levels, s->dtype,
                          g->device(), g->last_grid(), g->launches_per_solve(),
                          f.n_tasks, (int64_t) f.slab_bytes, f.n_slots, f.n_task_levels, f.n_stored_values,
-                         b.n_tasks, (int64_t) b.slab_bytes, b.n_slots, b.n_task_levels, b.n_stored_values};
+                         b.n_tasks, (int64_t) b.slab_bytes, b.n_slots, b.n_task_levels, b.n_stored_values,
+                         g->front() ? 1 : 0, f.n_w_rows, f.n_warps};
     int m = (int) (sizeof(v) / sizeof(v[0]));
     if (cap < m) m = cap;
     std::memcpy(out, v, sizeof(int64_t) * (size_t) m);
@@ -335,3 +353,39 @@ CHB_API int chb_schedule_sweep(const chb_schedule *s, int upper, const void **sl
     return m;
 }
 CHB_API void chb_schedule_destroy(chb_schedule *s) { delete s; }
+
+CHB_API int chb_front_schedule_create(chb_front_schedule **out, int dtype, int n, int64_t nnz_l, const int32_t *l_colptr,
+                                      const int32_t *l_rowidx, const double *l_vals, const int32_t *perm) {
+    return guarded([&] {
+        check_dtype(dtype);
+        chb::HostFactor L;
+        fill_factor(L, n, nnz_l, l_colptr, l_rowidx, l_vals, perm);
+        const int elem = dtype == CHB_F32 ? 4 : 8;
+        const chb::FrontOptions opt = chb::front_options_from_env(elem);
+        chb_front_schedule *s = new chb_front_schedule();
+        try {
+            chb::build_front_structure(L, elem, opt, &s->structure);
+            for (int upper = 0; upper < 2; ++upper) chb::build_front_image(L, s->structure, elem, upper != 0, opt, &s->sweep[upper]);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+    });
+}
+CHB_API int chb_front_schedule_sweep(const chb_front_schedule *s, int upper, const void **slab, const void **tasks,
+                                     const int32_t **order, int64_t *info, int cap) {
+    const chb::FrontImage &img = s->sweep[upper ? 1 : 0];
+    *slab = img.slab.data();
+    *tasks = img.tasks.data();
+    *order = img.order.data();
+    const int64_t v[] = {(int64_t) img.tasks.size(), (int64_t) img.slab.size(), img.page_bytes, img.tile_rows, img.n_w_rows,
+                         img.max_stage_rows, img.n_levels, img.n_values, img.n_stored_values, img.n_local_tasks,
+                         img.n_dense_tasks, img.n_mma, img.n_asm_entries, s->structure.ns, (int64_t) s->structure.locals.size(),
+                         s->structure.n_blocks, img.n_warps};
+    int m = (int) (sizeof(v) / sizeof(v[0]));
+    if (cap < m) m = cap;
+    std::memcpy(info, v, sizeof(int64_t) * (size_t) m);
+    return m;
+}
+CHB_API void chb_front_schedule_destroy(chb_front_schedule *s) { delete s; }

@@ -1,0 +1,696 @@
+// Front sweep kernels (sm_100a): forward (L y = P b) and backward (L' x = y, x -> P' x) triangular solves over the
+// supernodal task image built by front_schedule.cpp.  One kernel serves both sweeps (the record stream says what
+// to do); variants differ in element type and in the number of RHS columns a lane owns.
+//
+// What they replace: solve_lower_* / solve_upper_* of the reference (kernels/kernels.cu:64-131, 133-202: one
+// 128-thread CTA per ROW, one flag poll + two block barriers per non-zero, one lane per RHS column).
+//
+// Execution model
+//   * persistent co-resident grid; a CTA = 7 (or 4) COMPUTE warps + 1 LOADER warp; tickets are drawn from one atomic
+//     counter in a topological order of the task graph (forward progress: the oldest unfinished ticket always
+//     runs with its dependencies done);
+//   * the loader streams the task's record slab into a ring of pages with 1-D TMA bulk copies (factor bytes leave
+//     HBM exactly once per sweep), finds the staged records (FR_LOADX), polls their producers' ready flags
+//     (ld.acquire.gpu) and copies the rows they name -- solved rows, right-hand-side rows of the user's b through
+//     the permutation, rows of a local task -- into a shared-memory ROW RING with TMA bulk copies that complete
+//     on the record's mbarrier.  It runs ahead of the compute warps by the depth of the rings, across task
+//     boundaries;
+//   * DENSE steps (FR_MMA): a warp owns a tile of TR rows x all RHS columns (CPL columns per lane: TR x CPL
+//     accumulators in registers), and adds A(TR x s) X(s x n_rhs): X rows are read from the row ring (one
+//     conflict-free vector load per source row), the TR factor values of a source column are broadcast loads
+//     from the page.  Per source row and lane: 1 + TR/4 shared loads for TR x CPL fused multiply-adds
+//     (f32, 128 RHS: 5 loads per 64 FMAs), no index arithmetic, no per-block bookkeeping;
+//   * the epilogue (FR_EPI) writes tiles to the work vector / the update-row buffer / the user's x through P',
+//     or back into ring rows; FR_ASM subtracts the update rows addressed to the staged right-hand side
+//     (8 independent row loads in flight per warp); diagonal blocks are applied as explicit inverses (more MMAs);
+//   * LOCAL tasks (complete subtrees): rows staged once, substituted in place as sparse rows, one RHS column per
+//     lane, written back once;
+//   * dependencies: one epoch-valued ready flag per task, st.release.gpu after a barrier of the compute warps;
+//     flags are never cleared (the epoch is the solve counter);
+//   * proxies: rows written with generic stores and later read or overwritten by TMA are ordered with
+//     fence.proxy.async on both sides (after the acquire poll in the loader, before a staged record is released
+//     by the compute warps).
+#pragma once
+#include <cstdint>
+
+#include "kernel_args.h"
+
+namespace front {
+
+using chb::FrontArgs;
+using chb::SweepTask;
+
+constexpr int kStages = 3;       // pages in the CTA's slab ring
+constexpr int kRowBars = 16;     // staged records in flight
+constexpr int kTaskQueue = 4;    // task descriptors the loader may run ahead
+constexpr unsigned kFullMask = 0xffffffffu;
+
+enum : uint32_t { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE };
+enum : uint32_t { FE_RING_SUB = 1, FE_RING_SET = 2, FE_Y = 4, FE_W = 8, FE_DST = 16 };
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Watchdog: a dependency that never arrives (a schedule or kernel bug) raises the error word and ends the wait
+// instead of hanging the GPU or killing the context; the host reports it after the sweep (GpuSolver::check_error).
+constexpr unsigned long long kWatchdogNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *error_word) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return;
+        if ((spins & 1023u) == 1023u) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kWatchdogNs || *(volatile int *) error_word != 0) {
+                atomicExch(error_word, 1);
+                return;
+            }
+        }
+    }
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- CPL-wide vectors of one lane's columns ---------------------------------------------------------
+template <typename F, int N>
+struct alignas(sizeof(F) * N > 16 ? 16 : sizeof(F) * N) Vec {
+    F v[N];
+};
+// L2-coherent global accesses (rows written by other SMs in this launch or in earlier launches: never through L1)
+template <int BYTES>
+__device__ __forceinline__ void ldcg_bytes(void *dst, const void *src) {
+    if constexpr (BYTES == 4) {
+        *(uint32_t *) dst = __ldcg((const uint32_t *) src);
+    } else if constexpr (BYTES == 8) {
+        *(uint2 *) dst = __ldcg((const uint2 *) src);
+    } else if constexpr (BYTES == 16) {
+        *(uint4 *) dst = __ldcg((const uint4 *) src);
+    } else {
+        ((uint4 *) dst)[0] = __ldcg((const uint4 *) src);
+        ((uint4 *) dst)[1] = __ldcg((const uint4 *) src + 1);
+    }
+}
+template <int BYTES>
+__device__ __forceinline__ void stcg_bytes(void *dst, const void *src) {
+    if constexpr (BYTES == 4) {
+        __stcg((uint32_t *) dst, *(const uint32_t *) src);
+    } else if constexpr (BYTES == 8) {
+        __stcg((uint2 *) dst, *(const uint2 *) src);
+    } else if constexpr (BYTES == 16) {
+        __stcg((uint4 *) dst, *(const uint4 *) src);
+    } else {
+        __stcg((uint4 *) dst, ((const uint4 *) src)[0]);
+        __stcg((uint4 *) dst + 1, ((const uint4 *) src)[1]);
+    }
+}
+template <typename F, int N> __device__ __forceinline__ Vec<F, N> ld_global(const F *p) {
+    Vec<F, N> r;
+    ldcg_bytes<(int) sizeof(F) * N>(&r, p);
+    return r;
+}
+template <typename F, int N> __device__ __forceinline__ void st_global(F *p, const Vec<F, N> &v) {
+    stcg_bytes<(int) sizeof(F) * N>(p, &v);
+}
+template <typename F, int N> __device__ __forceinline__ Vec<F, N> ld_shared(const F *p) {
+    return *reinterpret_cast<const Vec<F, N> *>(p);
+}
+template <typename F, int N> __device__ __forceinline__ void st_shared(F *p, const Vec<F, N> &v) {
+    *reinterpret_cast<Vec<F, N> *>(p) = v;
+}
+
+template <typename F> struct Tile { static constexpr int rows = 16; };
+template <> struct Tile<double> { static constexpr int rows = 8; };
+
+struct QueuedTask {
+    int ticket;  // >= n_tasks: no more work
+    int task;    // id = index of the task's ready flag
+    unsigned int bytes;
+    unsigned int pad;
+};
+
+// Shared memory of one CTA (dynamic):
+//   [kStages][page]       slab ring (TMA destination)
+//   [ring_rows + 1][kp]   row ring
+//   full/empty[kStages], rfull/rempty[kRowBars], tfull/tempty[kTaskQueue], queue, rows_of, rows_base
+template <typename F>
+struct Smem {
+    unsigned char *slab;
+    F *ring;
+    uint64_t *full, *empty, *rfull, *rempty, *tfull, *tempty;
+    QueuedTask *queue;
+    int *rows_of, *rows_base;
+    __device__ __forceinline__ Smem(unsigned char *raw, int kp, int ring_rows, int page) {
+        slab = raw;
+        ring = reinterpret_cast<F *>(raw + (size_t) kStages * page);
+        full = reinterpret_cast<uint64_t *>(ring + (size_t) (ring_rows + 1) * kp);
+        empty = full + kStages;
+        rfull = empty + kStages;
+        rempty = rfull + kRowBars;
+        tfull = rempty + kRowBars;
+        tempty = tfull + kTaskQueue;
+        queue = reinterpret_cast<QueuedTask *>(tempty + kTaskQueue);
+        rows_of = reinterpret_cast<int *>(queue + kTaskQueue);
+        rows_base = rows_of + kRowBars;
+    }
+};
+
+// ---- the loader warp -------------------------------------------------------------------------------
+template <typename F, int NW>
+__device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F> &sm, int lane) {
+    const int k = a.k, kp = (k + 3) & ~3;
+    const int ring_rows = a.ring_rows;
+    const uint32_t page = (uint32_t) a.page_bytes;
+    const uint32_t row_bytes = (uint32_t) kp * (uint32_t) sizeof(F);
+    const uint32_t src_row_bytes = (uint32_t) k * (uint32_t) sizeof(F);
+    const bool src_tma = a.src_tma != 0;
+    const int epoch = a.epoch;
+    uint32_t issued = 0;      // pages handed to TMA so far
+    uint32_t j_issue = 0;     // staged records issued so far
+    uint32_t j_rel = 0;       // staged records known to be released by the compute warps
+    int rows_in_flight = 0;
+    int head = 0;
+    uint32_t q = 0;           // tasks queued so far
+
+    // current and next task (warp-uniform copies): descriptor + first global page
+    int t_cur = 0, t_next = 0;
+    SweepTask d_cur{0ull, 0u, 0u}, d_next{0ull, 0u, 0u};
+    uint32_t first_cur = 0, first_next = 0;
+    auto fetch = [&](int &t, SweepTask &d) {
+        int tt = 0;
+        unsigned long long off = 0;
+        unsigned int bytes = 0, id = 0;
+        if (lane == 0) {
+            tt = atomicAdd(a.ticket, 1);
+            if (tt < a.n_tasks) {
+                const SweepTask s = a.tasks[tt];
+                off = s.offset, bytes = s.bytes, id = s.level;
+            }
+        }
+        t = __shfl_sync(kFullMask, tt, 0);
+        d.offset = __shfl_sync(kFullMask, off, 0);
+        d.bytes = __shfl_sync(kFullMask, bytes, 0);
+        d.level = __shfl_sync(kFullMask, id, 0);
+    };
+    auto pages_of = [&](const SweepTask &d) { return (d.bytes + page - 1) / page; };
+    // hands pages to TMA in global order while the ring has room; blocks only for page `must` (the one needed now)
+    auto feed_pages = [&](uint32_t must) {
+        for (;;) {
+            // which task owns page `issued`?
+            const SweepTask *d;
+            uint32_t first;
+            if (issued < first_cur + pages_of(d_cur)) d = &d_cur, first = first_cur;
+            else if (t_next < a.n_tasks && issued < first_next + pages_of(d_next)) d = &d_next, first = first_next;
+            else break;
+            if (issued >= must + kStages) break;
+            const uint32_t st = issued % kStages, fill = issued / kStages;
+            if (fill > 0) {
+                if (issued <= must) {
+                    mbar_wait(sm.empty + st, (fill - 1) & 1, a.error);
+                } else {
+                    const int free_now = lane == 0 ? (int) mbar_test(sm.empty + st, (fill - 1) & 1) : 0;
+                    if (!__shfl_sync(kFullMask, free_now, 0)) break;
+                }
+            }
+            const uint32_t pi = issued - first;
+            const uint32_t bytes = min(page, d->bytes - pi * page);
+            if (lane == 0) {
+                mbar_expect_tx(sm.full + st, bytes);
+                tma_load_1d(sm.slab + (size_t) st * page, a.slab + d->offset + (size_t) pi * page, bytes, sm.full + st);
+            }
+            issued += 1;
+        }
+    };
+
+    fetch(t_cur, d_cur);
+    first_cur = 0;
+    for (;;) {
+        if (t_cur >= a.n_tasks) {
+            if (lane == 0) {
+                if (q >= kTaskQueue) mbar_wait(sm.tempty + q % kTaskQueue, ((q / kTaskQueue) - 1) & 1, a.error);
+                sm.queue[q % kTaskQueue] = QueuedTask{a.n_tasks, 0, 0u, 0u};
+                mbar_arrive(sm.tfull + q % kTaskQueue);
+            }
+            break;
+        }
+        const uint32_t n_pages = pages_of(d_cur);
+        // the next ticket is drawn now: its descriptor round trip and first pages overlap this task
+        fetch(t_next, d_next);
+        first_next = first_cur + n_pages;
+        if (lane == 0) {
+            if (q >= kTaskQueue) mbar_wait(sm.tempty + q % kTaskQueue, ((q / kTaskQueue) - 1) & 1, a.error);
+            sm.queue[q % kTaskQueue] = QueuedTask{t_cur, (int) d_cur.level, d_cur.bytes, 0u};
+            mbar_arrive(sm.tfull + q % kTaskQueue);
+        }
+        q += 1;
+        for (uint32_t pg = 0; pg < n_pages; ++pg) {
+            const uint32_t g = first_cur + pg, stage = g % kStages;
+            feed_pages(g);
+            __syncwarp();
+            mbar_wait(sm.full + stage, (g / kStages) & 1, a.error);
+            const unsigned char *p = sm.slab + (size_t) stage * page;
+            const unsigned char *pend = p + min(page, d_cur.bytes - pg * page);
+            while (p < pend) {
+                const uint4 h = *reinterpret_cast<const uint4 *>(p);
+                const unsigned char *rec = p;
+                p += (h.x >> 8) * 16;
+                if ((h.x & 0xff) != FR_LOADX) continue;
+                const int n_contig = (int) (h.y & 1023u), n_gather = (int) (h.y >> 10 & 1023u), n_extra = (int) (h.y >> 20 & 1023u);
+                const int cbuf = (int) (h.w & 15u), gkind = (int) (h.w >> 4 & 15u), n_wait = (int) (h.w >> 8);
+                const int *waits = reinterpret_cast<const int *>(rec + 16);
+                const int *glist = waits + ((n_wait + 3) & ~3);
+                // producers
+                for (int e = lane; e < n_wait; e += 32) {
+                    const int *flag = a.done + waits[e];
+                    unsigned spins = 0;
+                    unsigned long long t0 = 0;
+                    while (ld_acquire_gpu(flag) != epoch) {
+                        if ((++spins & 4095u) == 0) {
+                            const unsigned long long now = global_ns();
+                            if (t0 == 0) t0 = now;
+                            if (now - t0 > kWatchdogNs || *(volatile int *) a.error != 0) {
+                                atomicExch(a.error, 2);
+                                break;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                fence_proxy_async();  // the producers' generic-proxy stores are read through the async proxy (TMA) below
+                // ring space: a record's rows never wrap around the ring end; back-pressure on rows and barrier pairs
+                const int nr = n_contig + n_gather + n_extra;
+                int skipped = 0;
+                if (head + nr > ring_rows) skipped = ring_rows - head, head = 0;
+                while (j_issue - j_rel >= (uint32_t) kRowBars || (rows_in_flight > 0 && rows_in_flight + nr + skipped > ring_rows)) {
+                    mbar_wait(sm.rempty + j_rel % kRowBars, (j_rel / kRowBars) & 1, a.error);
+                    rows_in_flight -= sm.rows_of[j_rel % kRowBars];
+                    j_rel += 1;
+                }
+                __syncwarp();
+                const uint32_t slot = j_issue % kRowBars;
+                uint64_t *bar = sm.rfull + slot;
+                if (lane == 0) {
+                    sm.rows_of[slot] = nr + skipped;
+                    sm.rows_base[slot] = head;
+                }
+                uint32_t tx = 0;
+                if (n_contig > 0) {
+                    const F *from = (cbuf == 1 ? a.tmp : a.wbuf) + (size_t) (int) h.z * kp;
+                    if (lane == 0) tma_load_1d(sm.ring + (size_t) head * kp, from, (uint32_t) n_contig * row_bytes, bar);
+                    tx += (uint32_t) n_contig * row_bytes;
+                }
+                F *gdst = sm.ring + (size_t) (head + n_contig) * kp;
+                if (gkind == 1) {
+                    for (int i = lane; i < n_gather; i += 32) tma_load_1d(gdst + (size_t) i * kp, a.tmp + (size_t) glist[i] * kp, row_bytes, bar);
+                    tx += (uint32_t) n_gather * row_bytes;
+                } else if (gkind == 2) {
+                    if (src_tma) {
+                        for (int i = lane; i < n_gather; i += 32)
+                            tma_load_1d(gdst + (size_t) i * kp, a.src + (size_t) glist[i] * k, src_row_bytes, bar);
+                        tx += (uint32_t) n_gather * src_row_bytes;
+                    } else {
+                        const int total = n_gather * k;
+#pragma unroll 1
+                        for (int e = lane; e < total; e += 32) {
+                            const int i = e / k, c = e - i * k;
+                            gdst[(size_t) i * kp + c] = __ldg(a.src + (size_t) glist[i] * k + c);
+                        }
+                    }
+                }
+                __syncwarp();  // manual copies are complete before the arrival
+                if (lane == 0) mbar_expect_tx(bar, tx);
+                j_issue += 1;
+                rows_in_flight += nr + skipped;
+                head += nr;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sm.empty + stage);
+        }
+        // next task becomes current
+        t_cur = t_next;
+        d_cur = d_next;
+        first_cur = first_next;
+        t_next = a.n_tasks;
+    }
+}
+
+// ---- the compute warps -----------------------------------------------------------------------------
+template <typename F, int CPL, int NW>
+__device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F> &sm, int warp, int lane) {
+    constexpr int TR = Tile<F>::rows;
+    constexpr int AV = 16 / (int) sizeof(F);     // factor values per 16-byte shared load
+    using V = Vec<F, CPL>;
+    const int k = a.k, kp = (k + 3) & ~3;
+    const uint32_t page = (uint32_t) a.page_bytes;
+    const int col = lane * CPL;
+    const bool active = col < kp;
+    const int lcol = active ? col : 0;           // a column this lane may always read
+    const bool leader = warp == 0 && lane == 0;
+    const bool dst_vec = a.dst_vec != 0;
+
+    uint32_t gpage = 0;      // global index of the current task's first page
+    uint32_t j0 = 0;         // sequence number of the task's first staged record
+
+    // waits for staged record sj of the current task; returns its first ring row
+    auto staged = [&](uint32_t sj) -> int {
+        const uint32_t j = j0 + sj;
+        mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
+        return sm.rows_base[j % kRowBars];
+    };
+    auto store_dst = [&](int perm_row, const V &v) {
+        F *d = a.dst + (size_t) perm_row * k + col;
+        if (dst_vec) {
+            *reinterpret_cast<V *>(d) = v;
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+                if (col + c < k) d[c] = v.v[c];
+        }
+    };
+
+    for (uint32_t q = 0;; ++q) {
+        mbar_wait(sm.tfull + q % kTaskQueue, (q / kTaskQueue) & 1, a.error);
+        const QueuedTask cur = sm.queue[q % kTaskQueue];
+        if (cur.ticket >= a.n_tasks) break;
+        const int task = cur.task;
+        const uint32_t total = cur.bytes;
+        const uint32_t n_pages = (total + page - 1) / page;
+        if (a.trace && leader) a.trace[8 * (size_t) task] = global_ns();
+        uint32_t n_staged = 0;
+
+        // record cursor over the task's pages
+        uint32_t pg = 0, stage = 0;
+        const unsigned char *p = nullptr, *pend = nullptr;
+        bool page_open = false;
+        auto next_record = [&](uint4 &h, const unsigned char *&pay) -> bool {
+            while (p >= pend) {
+                if (page_open) {
+                    __syncwarp();  // every lane is done reading this stage
+                    if (lane == 0) mbar_arrive(sm.empty + stage);
+                    page_open = false;
+                }
+                if (pg == n_pages) return false;
+                const uint32_t g = gpage + pg;
+                stage = g % kStages;
+                mbar_wait(sm.full + stage, (g / kStages) & 1, a.error);
+                p = sm.slab + (size_t) stage * page;
+                pend = p + min(page, total - pg * page);
+                pg += 1;
+                page_open = true;
+            }
+            h = *reinterpret_cast<const uint4 *>(p);
+            pay = p + 16;
+            p += (h.x >> 8) * 16;
+            return true;
+        };
+        auto release = [&](uint32_t sj) {
+            // every compute warp passes here, in staging order; the wait keeps a fast warp from arriving on a
+            // barrier pair the loader has not recycled yet
+            const uint32_t j = j0 + sj;
+            mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
+            fence_proxy_async_smem();  // generic-proxy writes to these ring rows precede the TMA writes that reuse them
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sm.rempty + j % kRowBars);
+        };
+
+        uint4 h;
+        const unsigned char *pay;
+        while (next_record(h, pay)) {
+            uint32_t type = h.x & 0xff;
+            if (type == FR_MMA) {
+                // One accumulation: MMA records (interleaved with staging / release / barrier records) up to the
+                // epilogue.  The accumulators live only inside this block.
+                F acc[TR][CPL];
+                for (;;) {
+                    if (type == FR_MMA) {
+                        const int t = warp - (int) (h.y & 255u);
+                        if (t >= 0 && t < (int) (h.y >> 8 & 255u)) {
+                            const int n_src = (int) (h.y >> 16 & 255u);
+                            const int base = staged(h.z & 0xffffu) + (int) (h.z >> 16);
+                            if (h.y >> 24 & 1u) {
+#pragma unroll
+                                for (int i = 0; i < TR; ++i)
+#pragma unroll
+                                    for (int c = 0; c < CPL; ++c) acc[i][c] = F(0);
+                            }
+                            const F *A = reinterpret_cast<const F *>(pay) + (size_t) t * n_src * TR;
+                            const F *X = sm.ring + (size_t) base * kp + lcol;
+#pragma unroll 2
+                            for (int s = 0; s < n_src; ++s) {
+                                const V x = ld_shared<F, CPL>(X);
+                                X += kp;
+                                F av[TR];
+#pragma unroll
+                                for (int i = 0; i < TR; i += AV) {
+                                    const Vec<F, AV> q4 = ld_shared<F, AV>(A + i);
+#pragma unroll
+                                    for (int j = 0; j < AV; ++j) av[i + j] = q4.v[j];
+                                }
+                                A += TR;
+#pragma unroll
+                                for (int i = 0; i < TR; ++i)
+#pragma unroll
+                                    for (int c = 0; c < CPL; ++c) acc[i][c] = fma(av[i], x.v[c], acc[i][c]);
+                            }
+                        }
+                    } else if (type == FR_EPI) {
+                        const int t = warp - (int) (h.y & 255u);
+                        const uint32_t mode = h.y >> 16;
+                        if (t >= 0 && t < (int) (h.y >> 8 & 255u)) {
+                            const int r0 = t * TR;
+                            const int nvalid = min(TR, (int) (h.z & 0xffffu) - r0);
+                            const int *ip = reinterpret_cast<const int *>(pay);
+                            F *ring_row = nullptr;
+                            if (mode & (FE_RING_SUB | FE_RING_SET)) ring_row = sm.ring + (size_t) (staged(h.z >> 16) + ip[0] + r0) * kp + lcol;
+                            const size_t g0 = (size_t) ((int) h.w + r0);
+                            F *yrow = a.tmp + g0 * kp + lcol, *wrow = a.wbuf + g0 * kp + lcol;
+#pragma unroll
+                            for (int i = 0; i < TR; ++i) {
+                                if (i < nvalid && active) {
+                                    V v;
+#pragma unroll
+                                    for (int c = 0; c < CPL; ++c) v.v[c] = acc[i][c];
+                                    if (mode & FE_RING_SUB) {
+                                        const V o = ld_shared<F, CPL>(ring_row + (size_t) i * kp);
+#pragma unroll
+                                        for (int c = 0; c < CPL; ++c) v.v[c] = o.v[c] - v.v[c];
+                                        st_shared<F, CPL>(ring_row + (size_t) i * kp, v);
+                                    }
+                                    if (mode & FE_RING_SET) st_shared<F, CPL>(ring_row + (size_t) i * kp, v);
+                                    if (mode & FE_Y) st_global<F, CPL>(yrow + (size_t) i * kp, v);
+                                    if (mode & FE_W) st_global<F, CPL>(wrow + (size_t) i * kp, v);
+                                    if (mode & FE_DST) store_dst(ip[4 + r0 + i], v);
+                                }
+                            }
+                        }
+                        break;  // the epilogue ends the accumulation
+                    } else if (type == FR_REL) {
+                        release(h.y);
+                    } else if (type == FR_LOADX) {
+                        n_staged += 1;
+                    } else if (type == FR_BAR) {
+                        named_barrier(1, NW * 32);
+                    }
+                    if (!next_record(h, pay)) break;  // (malformed stream: an accumulation without epilogue)
+                    type = h.x & 0xff;
+                }
+            } else if (type == FR_ASM) {
+                // ring[row] -= W[w_row] for this warp's entries, 8 row loads in flight
+                const int *ip = reinterpret_cast<const int *>(pay);
+                const int lo = ip[warp], hi = ip[warp + 1];
+                if (lo < hi) {
+                    F *rows = sm.ring + (size_t) (staged(h.y & 0xffffu) + (int) (h.y >> 16)) * kp + lcol;
+                    const int2 *ent = reinterpret_cast<const int2 *>(ip + 12);
+                    for (int e = lo; e < hi; e += 8) {
+                        V vals[8];
+                        int rr[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int2 en = ent[min(e + j, hi - 1)];
+                            rr[j] = en.x;
+                            vals[j] = ld_global<F, CPL>(a.wbuf + (size_t) en.y * kp + lcol);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (e + j < hi && active) {
+                                F *dst = rows + (size_t) rr[j] * kp;
+                                V o = ld_shared<F, CPL>(dst);
+#pragma unroll
+                                for (int c = 0; c < CPL; ++c) o.v[c] -= vals[j].v[c];
+                                st_shared<F, CPL>(dst, o);
+                            }
+                        }
+                    }
+                }
+            } else if (type == FR_BAR) {
+                named_barrier(1, NW * 32);
+            } else if (type == FR_REL) {
+                release(h.y);
+            } else if (type == FR_LOADX) {
+                n_staged += 1;
+            } else if (type == FR_LROWS) {
+                // sparse rows of a local task, substituted in place, one RHS column per lane
+                const int lc = warp * 32 + lane;
+                if (warp * 32 < kp) {
+                    F *lrow = sm.ring + (size_t) staged(h.z) * kp + (lc < kp ? lc : warp * 32);
+                    const unsigned char *qp = pay;
+                    for (int i = 0; i < (int) h.y; ++i) {
+                        const uint32_t meta = *reinterpret_cast<const uint32_t *>(qp);
+                        const F pivot = *reinterpret_cast<const F *>(qp + 8);
+                        const int n4 = (int) (meta >> 8 & 0xff);
+                        const unsigned char *idx = qp + 16;
+                        const F *val = reinterpret_cast<const F *>(qp + 16 + ((4 * n4 + 15) & ~15));
+                        F *dst = lrow + (size_t) (meta & 0xff) * kp;
+                        F s = (meta >> 16 & 1) ? F(0) : *dst;
+                        for (int g4 = 0; g4 < n4; ++g4) {
+                            const uint32_t i4 = *reinterpret_cast<const uint32_t *>(idx + 4 * g4);
+                            F vv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j += AV) {
+                                const Vec<F, AV> v0 = ld_shared<F, AV>(val + 4 * g4 + j);
+#pragma unroll
+                                for (int jj = 0; jj < AV; ++jj) vv[j + jj] = v0.v[jj];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) s = fma(-vv[j], lrow[(size_t) (i4 >> (8 * j) & 0xff) * kp], s);
+                        }
+                        s = s * pivot;
+                        if (lc < kp) *dst = s;
+                        qp = reinterpret_cast<const unsigned char *>(val + 4 * n4);
+                    }
+                }
+            } else if (type == FR_LSTORE) {
+                const int n_int = (int) (h.y & 0xffffu), n_ext = (int) (h.y >> 16);
+                const int *ip = reinterpret_cast<const int *>(pay);
+                const F *rows = sm.ring + (size_t) staged(h.z) * kp + lcol;
+                if (active) {
+                    F *yrow = a.tmp + (size_t) (int) h.w * kp + col;
+                    for (int i = warp; i < n_int; i += NW) {
+                        const V v = ld_shared<F, CPL>(rows + (size_t) i * kp);
+                        st_global<F, CPL>(yrow + (size_t) i * kp, v);
+                        if (a.dst) store_dst(ip[4 + i], v);
+                    }
+                    F *wrow = a.wbuf + (size_t) ip[0] * kp + col;
+                    for (int e = warp; e < n_ext; e += NW) st_global<F, CPL>(wrow + (size_t) e * kp, ld_shared<F, CPL>(rows + (size_t) (n_int + e) * kp));
+                }
+            }
+            // FR_NOP: nothing
+        }
+        gpage += n_pages;
+        j0 += n_staged;
+
+        // publish: every compute warp's stores of this task are done before the flag is released
+        named_barrier(1, NW * 32);
+        if (leader) {
+            if (a.trace) a.trace[8 * (size_t) task + 2] = global_ns();
+            st_release_gpu(a.done + task, a.epoch);
+            mbar_arrive(sm.tempty + q % kTaskQueue);
+        }
+    }
+}
+
+template <typename F, int CPL, int NW>
+__device__ __forceinline__ void front_worker(const FrontArgs<F> &a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int kp = (a.k + 3) & ~3;
+    const Smem<F> sm(smem_raw, kp, a.ring_rows, a.page_bytes);
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) *a.ticket_next = 0;
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(sm.full + s, 1);
+            mbar_init(sm.empty + s, NW + 1);
+        }
+#pragma unroll
+        for (int s = 0; s < kRowBars; ++s) {
+            mbar_init(sm.rfull + s, 1);
+            mbar_init(sm.rempty + s, NW);
+        }
+#pragma unroll
+        for (int s = 0; s < kTaskQueue; ++s) {
+            mbar_init(sm.tfull + s, 1);
+            mbar_init(sm.tempty + s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == NW) loader_warp<F, NW>(a, sm, lane);
+    else compute_warp<F, CPL, NW>(a, sm, warp, lane);
+}
+
+}  // namespace front
+
+// Two CTA shapes: 7 compute warps + loader (256 threads, 2 CTAs per SM) and 4 + loader (160 threads, 3 per SM);
+// both leave 128 registers per thread (4 warps per scheduler).  The image is built for one of them (n_warps).
+#define CHB_FRONT(NAME, T, CPL, NW, MINB)                                                                \
+    extern "C" __global__ void __launch_bounds__(32 * (NW + 1), MINB) NAME(const chb::FrontArgs<T> a) {   \
+        front::front_worker<T, CPL, NW>(a);                                                              \
+    }
+
+CHB_FRONT(chb_front_f32_c1_w7, float, 1, 7, 2)
+CHB_FRONT(chb_front_f32_c2_w7, float, 2, 7, 2)
+CHB_FRONT(chb_front_f32_c4_w7, float, 4, 7, 2)
+CHB_FRONT(chb_front_f64_c1_w7, double, 1, 7, 2)
+CHB_FRONT(chb_front_f64_c2_w7, double, 2, 7, 2)
+CHB_FRONT(chb_front_f64_c4_w7, double, 4, 7, 2)
+CHB_FRONT(chb_front_f32_c1_w4, float, 1, 4, 3)
+CHB_FRONT(chb_front_f32_c2_w4, float, 2, 4, 3)
+CHB_FRONT(chb_front_f32_c4_w4, float, 4, 4, 3)
+CHB_FRONT(chb_front_f64_c1_w4, double, 1, 4, 3)
+CHB_FRONT(chb_front_f64_c2_w4, double, 2, 4, 3)
+CHB_FRONT(chb_front_f64_c4_w4, double, 4, 4, 3)

@@ -22,9 +22,15 @@ constexpr int kSweepTaskQueue = 8;   // sweep.cuh: kTaskQueue
 constexpr int kFuncAttrMaxDynamicSharedSize = 8;  // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES
 constexpr int kFuncAttrSharedCarveout = 9;        // CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT (percent)
 
+// Throws on failure: a null work buffer must never reach a kernel launch (it would fault the device and poison the
+// primary context shared with the caller's framework).
 void *dev_alloc(size_t bytes) {
     void *p = nullptr;
-    cuda_check(cuMemAlloc(&p, std::max<size_t>(bytes, 16)));
+    const CUresult rc = cuMemAlloc(&p, std::max<size_t>(bytes, 16));
+    if (rc != CUDA_SUCCESS || !p) {
+        cuda_check(rc);
+        throw std::runtime_error("out of device memory (cuMemAlloc of " + std::to_string(bytes) + " bytes failed)");
+    }
     return p;
 }
 void dev_free(void *&p) {
@@ -97,6 +103,41 @@ size_t sweep_smem_bytes(int elem, int k, int local_rows) {
            (2 * kSweepStages + 2 * kSweepRowBars + 2 * kSweepTaskQueue) * 8 + kSweepTaskQueue * 32 + kSweepRowBars * 4;
 }
 
+// -- front kernels (front_sweep.cuh) --------------------------------------------------------------
+constexpr int kFrontStages = 3;      // front_sweep.cuh: kStages
+constexpr int kFrontRowBars = 16;    // kRowBars
+constexpr int kFrontTaskQueue = 4;   // kTaskQueue
+constexpr size_t kSmemPerSm = 233472, kSmemReservedPerCta = 1024;
+
+int front_cpl(int k) {
+    const int kp = padded_rhs(k);
+    int cpl = kp <= 32 ? 1 : kp <= 64 ? 2 : 4;
+    if (const char *v = std::getenv("CHB_FRONT_CPL")) {
+        const int c = std::atoi(v);
+        if ((c == 1 || c == 2 || c == 4) && c * 32 >= kp) cpl = c;
+    }
+    return cpl;
+}
+size_t front_fixed_smem(int page_bytes) {
+    return (size_t) kFrontStages * (size_t) page_bytes + (2 * kFrontStages + 2 * kFrontRowBars + 2 * kFrontTaskQueue) * 8 +
+           kFrontTaskQueue * 16 + 2 * kFrontRowBars * 4 + 64;
+}
+// Rows of the row ring: what the CTA shape's share of the SM's shared memory holds (2 CTAs per SM with 7 compute
+// warps, 3 with 4), at most a few chunks beyond the largest staged record for narrow right-hand sides.
+int front_ring_rows(int elem, int k, int page_bytes, int n_warps, int max_stage_rows) {
+    const size_t row_bytes = (size_t) padded_rhs(k) * (size_t) elem;
+    const int ctas = n_warps == 4 ? 3 : 2;
+    const size_t budget = kSmemPerSm / ctas - kSmemReservedPerCta - front_fixed_smem(page_bytes);
+    int rows = (int) (budget / row_bytes) - 1;
+    if (const char *v = std::getenv("CHB_FRONT_RING_ROWS")) rows = std::min(rows, std::max(1, std::atoi(v)));
+    rows = std::min(rows, std::max(256, max_stage_rows + 4 * kFrontLoad));
+    if (rows < max_stage_rows) throw std::runtime_error("front sweep: the largest staged record does not fit the shared-memory row ring");
+    return rows;
+}
+size_t front_smem_bytes(int elem, int k, int page_bytes, int ring_rows) {
+    return front_fixed_smem(page_bytes) + (size_t) (ring_rows + 1) * (size_t) padded_rhs(k) * (size_t) elem;
+}
+
 }  // namespace
 
 void ImageShape::to_words(int64_t *w) const {
@@ -108,6 +149,9 @@ void ImageShape::to_words(int64_t *w) const {
     }
     w[14] = exact_order;
     w[15] = n_contrib_rows;
+    w[16] = front;
+    for (int u = 0; u < 2; ++u) w[17 + u] = n_w_rows[u], w[19 + u] = max_stage_rows[u];
+    w[21] = n_warps, w[22] = page_bytes, w[23] = 0;
 }
 ImageShape ImageShape::from_words(const int64_t *w) {
     ImageShape s;
@@ -119,6 +163,9 @@ ImageShape ImageShape::from_words(const int64_t *w) {
     }
     s.exact_order = w[14];
     s.n_contrib_rows = w[15];
+    s.front = w[16];
+    for (int u = 0; u < 2; ++u) s.n_w_rows[u] = w[17 + u], s.max_stage_rows[u] = w[19 + u];
+    s.n_warps = w[21], s.page_bytes = w[22];
     return s;
 }
 
@@ -178,6 +225,28 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
     sync0();
 }
 
+void GpuSolver::upload_front(SweepDev &d, const FrontImage &img) {
+    static_assert(sizeof(SweepTask) == sizeof(TaskDesc), "host and device task descriptors must match");
+    d.n_tasks = (int) img.tasks.size();
+    d.slab_bytes = img.slab.size();
+    d.n_task_levels = img.n_levels;
+    d.n_stored_values = img.n_stored_values;
+    d.n_w_rows = img.n_w_rows;
+    d.max_stage_rows = img.max_stage_rows;
+    d.page_bytes = img.page_bytes;
+    d.n_warps = img.n_warps;
+    allocate_sweep(d);
+    // device task table in ticket order; the `level` word carries the task id (its flag index)
+    std::vector<TaskDesc> by_ticket(img.tasks.size());
+    for (size_t t = 0; t < img.order.size(); ++t) {
+        by_ticket[t] = img.tasks[(size_t) img.order[t]];
+        by_ticket[t].level = (uint32_t) img.order[t];
+    }
+    h2d(d.slab, img.slab.data(), img.slab.size());
+    h2d(d.tasks, by_ticket.data(), sizeof(TaskDesc) * by_ticket.size());
+    sync0();
+}
+
 void GpuSolver::analyze(TriangleAnalysis &t, const std::vector<int> &ptr, const std::vector<int> &idx, bool lower) {
     int *counters = (int *) m_counters;
     void *rowptr_d = dev_alloc(sizeof(int) * ptr.size());
@@ -225,18 +294,26 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     m_perm_host = L.perm;
 
     // Host: lay the factor out as the two sweep images (one thread each) while the device runs the
-    // level analysis of both triangles.
+    // level analysis of both triangles.  Default: the front image (front_schedule.h); round 1's panel image keeps
+    // the reference's summation order (CHB_EXACT_ORDER=1) and stays selectable with CHB_SWEEP=panel.
     const ScheduleOptions opt = schedule_options_from_env();
     m_exact = opt.exact_order;
+    const char *mode = std::getenv("CHB_SWEEP");
+    m_front = !m_exact && !(mode && std::strcmp(mode, "panel") == 0);
+    const FrontOptions fopt = front_options_from_env(m_elem);
     PanelStructure structure;
-    build_panel_structure(L, opt, &structure);
+    FrontStructure fstructure;
+    if (m_front) build_front_structure(L, m_elem, fopt, &fstructure);
+    else build_panel_structure(L, opt, &structure);
     SweepImage img[2];
+    FrontImage fimg[2];
     std::exception_ptr errors[2];
     std::thread builders[2];
     for (int u = 0; u < 2; ++u)
         builders[u] = std::thread([&, u] {
             try {
-                build_sweep_image(L, structure, m_elem, u == 1, opt, &img[u]);
+                if (m_front) build_front_image(L, fstructure, m_elem, u == 1, fopt, &fimg[u]);
+                else build_sweep_image(L, structure, m_elem, u == 1, opt, &img[u]);
             } catch (...) {
                 errors[u] = std::current_exception();
             }
@@ -256,8 +333,13 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     for (int u = 0; u < 2; ++u)
         if (errors[u]) std::rethrow_exception(errors[u]);
     for (int u = 0; u < 2; ++u) {
-        upload_sweep(m_sweep[u], img[u]);
-        img[u] = SweepImage();
+        if (m_front) {
+            upload_front(m_sweep[u], fimg[u]);
+            fimg[u] = FrontImage();
+        } else {
+            upload_sweep(m_sweep[u], img[u]);
+            img[u] = SweepImage();
+        }
     }
     if (cuda_first_error() != CUDA_SUCCESS) throw std::runtime_error(driver_error_text());
 }
@@ -273,9 +355,14 @@ GpuSolver::GpuSolver(int device, int elem_size, const ImageShape &shape)
         m_sweep[u].n_slots = (int) shape.n_slots[u];
         m_sweep[u].n_task_levels = (int) shape.n_task_levels[u];
         m_sweep[u].max_local_rows = (int) shape.max_local_rows[u];
+        m_sweep[u].n_w_rows = shape.n_w_rows[u];
+        m_sweep[u].max_stage_rows = (int) shape.max_stage_rows[u];
+        m_sweep[u].page_bytes = (int) shape.page_bytes;
+        m_sweep[u].n_warps = (int) shape.n_warps;
         allocate_sweep(m_sweep[u]);
     }
     m_exact = shape.exact_order != 0;
+    m_front = shape.front != 0;
     m_sweep[0].n_contrib_rows = shape.n_contrib_rows;
     m_lower.n_levels = (int) shape.n_levels[0];
     m_upper.n_levels = (int) shape.n_levels[1];
@@ -297,6 +384,7 @@ GpuSolver::~GpuSolver() {
     dev_free(m_scratch);
     dev_free(m_rbuf);
     dev_free(m_cbuf);
+    dev_free(m_wbuf);
     dev_free(m_stage_b);
     dev_free(m_stage_x);
     if (m_copy_in) {
@@ -321,6 +409,9 @@ ImageShape GpuSolver::shape() const {
     }
     s.exact_order = m_exact ? 1 : 0;
     s.n_contrib_rows = m_sweep[0].n_contrib_rows;
+    s.front = m_front ? 1 : 0;
+    for (int u = 0; u < 2; ++u) s.n_w_rows[u] = m_sweep[u].n_w_rows, s.max_stage_rows[u] = m_sweep[u].max_stage_rows;
+    s.n_warps = m_sweep[0].n_warps, s.page_bytes = m_sweep[0].page_bytes;
     s.n_levels[0] = m_lower.n_levels;
     s.n_levels[1] = m_upper.n_levels;
     return s;
@@ -391,6 +482,68 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
     cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, block, 1, 1, (unsigned) smem, nullptr, params));
 }
 
+void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst) {
+    const SweepDev &s = m_sweep[upper ? 1 : 0];
+    char name[64];
+    snprintf(name, sizeof name, "chb_front_%s_c%d_w%d", m_elem == 4 ? "f32" : "f64", front_cpl(k), s.n_warps);
+    CUfunction fn = kernel(m_dev, name);
+    if (!fn) throw std::runtime_error(driver_error_text());
+    const int max_stage = std::max(m_sweep[0].max_stage_rows, m_sweep[1].max_stage_rows);
+    const int ring_rows = front_ring_rows(m_elem, k, s.page_bytes, s.n_warps, max_stage);
+    const size_t smem = front_smem_bytes(m_elem, k, s.page_bytes, ring_rows);
+    const int block = 32 * (s.n_warps + 1);
+    cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
+    cuda_check(cuFuncSetAttribute(fn, kFuncAttrSharedCarveout, 100));
+
+    int *counters = (int *) m_counters;
+    int *ticket = counters + (m_sweeps & 1), *ticket_next = counters + ((m_sweeps + 1) & 1);
+    m_sweeps += 1;
+    auto fill = [&](auto &a) {
+        using A = std::remove_reference_t<decltype(a)>;
+        using Float = std::remove_pointer_t<decltype(A::tmp)>;
+        a.n_tasks = s.n_tasks;
+        a.k = k;
+        a.epoch = m_epoch;
+        a.ring_rows = ring_rows;
+        a.page_bytes = s.page_bytes;
+        a.src_tma = (((uintptr_t) src & 15) == 0 && ((size_t) k * (size_t) m_elem) % 16 == 0) ? 1 : 0;
+        a.dst_vec = (((uintptr_t) dst & 15) == 0 && k % 4 == 0) ? 1 : 0;
+        a.slab = (const unsigned char *) s.slab;
+        a.tasks = (const SweepTask *) s.tasks;
+        a.done = (int *) s.done;
+        a.ticket = ticket;
+        a.ticket_next = ticket_next;
+        a.error = counters + 4;
+        a.tmp = (Float *) m_tmp;
+        a.wbuf = (Float *) m_wbuf;
+        a.src = (const Float *) src;
+        a.dst = (Float *) dst;
+        a.trace = (unsigned long long *) s.trace;
+    };
+    FrontArgs<float> a32;
+    FrontArgs<double> a64;
+    void *params[1];
+    if (m_elem == 4) {
+        fill(a32);
+        params[0] = &a32;
+    } else {
+        fill(a64);
+        params[0] = &a64;
+    }
+    int grid = std::max(1, std::min(s.n_tasks, max_resident_blocks(m_dev, fn, block, smem)));
+    if (const char *cap = std::getenv("CHB_SWEEP_CTAS_PER_SM")) grid = std::max(1, std::min(grid, std::atoi(cap) * m_dev->sm_count));
+    m_last_grid = grid;
+    cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, block, 1, 1, (unsigned) smem, nullptr, params));
+}
+
+int GpuSolver::device_error() {
+    ContextGuard guard(m_dev);
+    int word = 0;
+    d2h(&word, (int *) m_counters + 4, sizeof(int));
+    sync0();
+    return word;
+}
+
 void GpuSolver::solve(int k, const void *b, void *x) {
     if (k != m_k) {
         if (k > 128) throw std::invalid_argument("The number of RHS should be less than 128.");
@@ -403,18 +556,32 @@ void GpuSolver::solve(int k, const void *b, void *x) {
             dev_free(m_scratch);
             dev_free(m_rbuf);
             dev_free(m_cbuf);
-            m_kp_cap = padded_rhs(k);
-            m_cbuf = dev_alloc((size_t) m_elem * (size_t) m_sweep[0].n_contrib_rows * (size_t) m_kp_cap);
-            m_rbuf = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) m_kp_cap);
-            m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) m_kp_cap);
-            const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
-            m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) m_kp_cap);
+            dev_free(m_wbuf);
+            m_kp_cap = 0;  // (stays 0 if an allocation below throws: the next call starts over)
+            m_k = 0;
+            const int kp_new = padded_rhs(k);
+            m_tmp = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) kp_new);
+            if (m_front) {
+                const size_t w_rows = (size_t) std::max(m_sweep[0].n_w_rows, m_sweep[1].n_w_rows);
+                m_wbuf = dev_alloc((size_t) m_elem * w_rows * (size_t) kp_new);
+            } else {
+                m_cbuf = dev_alloc((size_t) m_elem * (size_t) m_sweep[0].n_contrib_rows * (size_t) kp_new);
+                m_rbuf = dev_alloc((size_t) m_elem * (size_t) m_n * (size_t) kp_new);
+                const size_t slots = (size_t) std::max(m_sweep[0].n_slots, m_sweep[1].n_slots);
+                m_scratch = dev_alloc((size_t) m_elem * slots * (size_t) kPanelWidth * (size_t) kp_new);
+            }
+            m_kp_cap = kp_new;
         }
         m_k = k;
     }
     m_epoch += 1;
-    sweep(false, k, b, nullptr);  // tmp = L^-1 P b
-    sweep(true, k, nullptr, x);   // x = P' L^-T tmp
+    if (m_front) {
+        front_sweep(false, k, b, nullptr);  // tmp = L^-1 P b
+        front_sweep(true, k, nullptr, x);   // x = P' L^-T tmp
+    } else {
+        sweep(false, k, b, nullptr);
+        sweep(true, k, nullptr, x);
+    }
 }
 
 // Host buffers end to end.  RHS columns are independent, so for k >= 64 the columns are processed in two (up to

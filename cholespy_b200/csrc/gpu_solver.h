@@ -10,6 +10,7 @@
 
 #include "cuda_driver.h"
 #include "factor_host.h"
+#include "front_schedule.h"
 #include "panel_schedule.h"
 
 namespace chb {
@@ -34,6 +35,11 @@ struct SweepDev {
     int max_local_rows = 0;  // largest local task (rows held in shared memory)
     int64_t n_contrib_rows = 0;  // rows of the contribution buffer this sweep writes (forward only)
     int64_t n_stored_values = 0;
+    // front images (front_schedule.h)
+    int64_t n_w_rows = 0;    // rows of the update-row buffer this sweep uses
+    int max_stage_rows = 0;  // largest staged record (lower bound of the row ring)
+    int page_bytes = 0;
+    int n_warps = 0;         // compute warps of the CTA shape the image was built for
 };
 
 struct ImageBuffer {
@@ -50,7 +56,10 @@ struct ImageShape {
     int64_t max_local_rows[2] = {0, 0};
     int64_t exact_order = 0;  // the image was built with ScheduleOptions::exact_order (selects the *_exact kernels)
     int64_t n_contrib_rows = 0;  // rows of the forward sweep's contribution buffer
-    static constexpr int kWords = 16;
+    int64_t front = 0;           // the image is a front image (front_schedule.h; selects the chb_front_* kernels)
+    int64_t n_w_rows[2] = {0, 0}, max_stage_rows[2] = {0, 0};
+    int64_t n_warps = 0, page_bytes = 0;
+    static constexpr int kWords = 24;
     void to_words(int64_t *w) const;
     static ImageShape from_words(const int64_t *w);
 };
@@ -83,6 +92,10 @@ public:
     const std::vector<int> &perm_host() const { return m_perm_host; }
     int last_grid() const { return m_last_grid; }
     int launches_per_solve() const { return 2; }
+    bool front() const { return m_front; }
+    // Blocks until the legacy stream is idle and returns the sweep watchdog's error word (0: fine; non-zero: a
+    // dependency never arrived -- a schedule or kernel bug; the results of the last solves are invalid).
+    int device_error();
     const SweepDev &sweep_image(bool upper) const { return m_sweep[upper ? 1 : 0]; }
     ImageShape shape() const;
     // Debug timeline of the last solve (CHB_TRACE=1): 8 x n_tasks words, see kernel_args.h.  Returns words copied.
@@ -96,6 +109,8 @@ private:
     void analyze(TriangleAnalysis &t, const std::vector<int> &ptr, const std::vector<int> &idx, bool lower);
     void upload_sweep(SweepDev &d, const SweepImage &img);
     void sweep(bool upper, int k, const void *src, void *dst);
+    void front_sweep(bool upper, int k, const void *src, void *dst);
+    void upload_front(SweepDev &d, const FrontImage &img);
 
     DeviceState *m_dev = nullptr;
     int m_elem = 4;
@@ -106,12 +121,14 @@ private:
     int m_sweeps = 0;
     int m_last_grid = 0;
     bool m_exact = false;       // exact-order schedule: packed triangles + IEEE division (the *_exact kernels)
+    bool m_front = true;        // front image + chb_front_* kernels (default); false: round 1's panel image (exact order, CHB_SWEEP=panel)
 
     TriangleAnalysis m_lower, m_upper;
     std::vector<int> m_perm_host;
     SweepDev m_sweep[2];        // [0] forward (L), [1] backward (L')
 
-    void *m_counters = nullptr; // int32[8]: [0,1] sweep tickets, [2] analysis ticket, [3] analysis max level
+    void *m_counters = nullptr; // int32[8]: [0,1] sweep tickets, [2] analysis ticket, [3] analysis max level, [4] watchdog error word
+    void *m_wbuf = nullptr;     // Float[n_w_rows*round4(k)]: update rows / partial products of the front sweeps
     void *m_tmp = nullptr;      // Float[n*k]
     void *m_rbuf = nullptr;     // Float[n*round4(k)]: residuals of the inverse super-blocks
     void *m_cbuf = nullptr;     // Float[n_contrib_rows*round4(k)]: forward contributions of the local tasks

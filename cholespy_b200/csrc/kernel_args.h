@@ -45,4 +45,27 @@ struct SweepArgs {
     unsigned long long *trace;  // optional (debug): 8 words per task {start ns, slab ready ns, end ns, cycles spent waiting, last wait ns, blocks done ns, triangle done ns, -}
 };
 
+// One front sweep (front_sweep.cuh: chb_front_*).  See front_schedule.h for the record format.
+template <typename Float>
+struct FrontArgs {
+    int n_tasks;
+    int k;
+    int epoch;
+    int ring_rows;        // rows of the shared-memory row ring (>= the largest staged record)
+    int page_bytes;       // slab page size (front_schedule.h: front_page_bytes)
+    int src_tma;          // rows of the user's b can be fetched by TMA (16-byte aligned, 16-byte multiples)
+    int dst_vec;          // rows of the user's x can be written with vector stores
+    const unsigned char *slab;
+    const SweepTask *tasks;     // ticket-ordered; `level` = task id = index of its ready flag
+    int *done;            // per-task epoch flags
+    int *ticket;          // this sweep's ticket counter
+    int *ticket_next;     // the other sweep's counter: cleared here
+    int *error;           // raised by the watchdog when a dependency never arrives (0 = fine)
+    Float *tmp;           // (n, round4(k)) work vector in permuted order: y after the forward sweep, x after the backward
+    Float *wbuf;          // (n_w_rows, round4(k)) update rows / partial products
+    const Float *src;     // forward: user's b;  backward: null
+    Float *dst;           // backward: user's x;  forward: null
+    unsigned long long *trace;  // optional (debug): 8 words per task {start ns, -, end ns, ...}
+};
+
 }  // namespace chb

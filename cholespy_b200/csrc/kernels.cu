@@ -3,7 +3,8 @@
 //
 // What they replace (reference: kernels/kernels.cu):
 //   chb_analysis            <- analysis_lower / analysis_upper   (:8-33, :35-60)
-//   chb_sweep_*  (sweep.cuh) <- solve_lower_* / solve_upper_*    (:64-131, :133-202)
+//   chb_front_*  (front_sweep.cuh) <- solve_lower_* / solve_upper_*  (:64-131, :133-202)   [default]
+//   chb_sweep_*  (sweep.cuh)       <- the same, reference summation order (CHB_EXACT_ORDER=1)
 //
 // chb_analysis: persistent co-resident grid, one warp per row, rows handed out in order by an atomic
 // ticket; the level word doubles as the ready flag (pre-set to -1), so a waiting row can never read a
@@ -76,3 +77,4 @@ extern "C" __global__ void __launch_bounds__(256) chb_analysis(const AnalysisArg
 }
 
 #include "sweep.cuh"
+#include "front_sweep.cuh"

@@ -76,12 +76,17 @@ int chb_solver_solve_cuda(chb_solver *s, int n_rhs, const void *b_dev, void *x_d
 int chb_solver_solve_host(chb_solver *s, int n_rhs, const void *b_host, void *x_host);
 /* CHOLMOD solve on the host for CPU-mode solvers.  Replaces solve_cpu (src/cholesky_solver.cpp:434-463). */
 int chb_solver_solve_cpu(chb_solver *s, int n_rhs, const void *b, void *x);
+/* Blocks until the device is idle and reports whether the sweep kernels' watchdog fired (a task dependency that
+ * never arrived: CHB_ERR_RUNTIME).  New: the reference's kernels spin forever in that case
+ * (kernels/kernels.cu:96-98). */
+int chb_solver_check_error(chb_solver *s);
 /* Replaces CholeskySolver<Float>::is_cpu (src/cholesky_solver.h:47). */
 int chb_solver_is_cpu(const chb_solver *s);
 
 /* Introspection: out[0..] = n, nnz(L), n_levels(lower), n_levels(upper), dtype, device,
  * grid size of the last sweep, kernel launches per solve, then per sweep (forward, backward):
- * n_tasks, slab bytes, scratch slots, task levels, stored values.  Returns the number of values written. */
+ * n_tasks, slab bytes, scratch slots, task levels, stored values; then 1 if the image is a front image
+ * (csrc/front_schedule.h), its update rows and the compute warps of its CTA shape.  Returns the number of values written. */
 int chb_solver_info(const chb_solver *s, int64_t *out, int cap);
 /* Analysis products of analyze_cuda (src/cholesky_solver.cpp:341-370), for bit-exact parity checks:
  * level_of_row[n] (the reference's level_ind) and order[n] (the reference's levels array). */
@@ -106,7 +111,7 @@ void chb_factor_destroy(chb_factor *f);
  * orders): build the solver on one GPU, read its shape, create empty replicas of the same shape on
  * the others, and broadcast each image buffer (NCCL) from the source into the replica.  New; the
  * reference is single-GPU.  shape = CHB_IMAGE_SHAPE_WORDS int64 words. */
-#define CHB_IMAGE_SHAPE_WORDS 16
+#define CHB_IMAGE_SHAPE_WORDS 24
 int chb_solver_image_shape(const chb_solver *s, int64_t *shape, int cap);
 int chb_solver_create_replica(chb_solver **out, int dtype, const int64_t *shape, int n_words, int device);
 int chb_solver_image_count(const chb_solver *s);
@@ -125,6 +130,19 @@ int chb_schedule_create(chb_schedule **out, int dtype, int n, int64_t nnz_l, con
 int chb_schedule_sweep(const chb_schedule *s, int upper, const void **slab, const void **tasks, const int32_t **order,
                        int64_t *info, int cap);
 void chb_schedule_destroy(chb_schedule *s);
+
+/* Host-side export of the FRONT schedule (csrc/front_schedule.h), the image the default sweep kernels stream:
+ * maximal supernodes as dense block columns, complete subtrees as shared-memory local tasks, update rows
+ * instead of per-block gathers.  Needs no GPU; interpreted by oracle/front_emulator.cpp in the CPU tests.
+ * info[0..16] = n_tasks, slab bytes, page bytes, tile rows, update rows (W), largest staged record, task levels,
+ * n_values, n_stored_values, local tasks, dense tasks, MMA records, assembly entries, supernodes, local task
+ * count, ticket-order blocks, compute warps of the CTA shape. */
+typedef struct chb_front_schedule chb_front_schedule;
+int chb_front_schedule_create(chb_front_schedule **out, int dtype, int n, int64_t nnz_l, const int32_t *l_colptr,
+                              const int32_t *l_rowidx, const double *l_vals, const int32_t *perm);
+int chb_front_schedule_sweep(const chb_front_schedule *s, int upper, const void **slab, const void **tasks,
+                             const int32_t **order, int64_t *info, int cap);
+void chb_front_schedule_destroy(chb_front_schedule *s);
 
 #ifdef __cplusplus
 }

@@ -232,3 +232,63 @@ def schedule_solve(lib, l_colptr, l_rowidx, l_vals, perm, b, exact_order=-1):
     finally:
         lib.chb_schedule_destroy(h)
     return x.reshape(b.shape), infos[0], infos[1]
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU interpreter of the product's FRONT schedule (oracle/front_emulator.cpp).
+# --------------------------------------------------------------------------------------------------
+_FRONT_EMU_SO = os.path.join(_HERE, "libfront_emu.so")
+_front_emu = None
+
+FRONT_INFO_KEYS = ("n_tasks", "slab_bytes", "page_bytes", "tile_rows", "n_w_rows", "max_stage_rows", "n_levels", "n_values",
+                   "n_stored_values", "n_local_tasks", "n_dense_tasks", "n_mma", "n_asm_entries", "n_supernodes", "n_locals",
+                   "n_blocks", "n_warps")
+
+
+def _load_front_emu():
+    global _front_emu
+    if _front_emu is None:
+        if not os.path.exists(_FRONT_EMU_SO):
+            build()
+        _front_emu = ctypes.CDLL(_FRONT_EMU_SO)
+    return _front_emu
+
+
+def front_schedule_solve(lib, l_colptr, l_rowidx, l_vals, perm, b):
+    """Builds the front schedule on the host (C ABI: chb_front_schedule_create) and executes both sweeps with the
+    sequential CPU interpreter.  Returns (x, info_forward, info_backward)."""
+    emu = _load_front_emu()
+    dt = b.dtype
+    assert dt in (np.float32, np.float64)
+    n = len(l_colptr) - 1
+    k = 1 if b.ndim == 1 else b.shape[1]
+    l_colptr = np.ascontiguousarray(l_colptr, np.int32)
+    l_rowidx = np.ascontiguousarray(l_rowidx, np.int32)
+    l_vals = np.ascontiguousarray(l_vals, np.float64)
+    perm = np.ascontiguousarray(perm, np.int32)
+    h = ctypes.c_void_p()
+    rc = lib.chb_front_schedule_create(ctypes.byref(h), 0 if dt == np.float32 else 1, n, len(l_rowidx), _p(l_colptr),
+                                       _p(l_rowidx), _p(l_vals), _p(perm))
+    if rc:
+        raise RuntimeError(lib.chb_last_error().decode())
+    try:
+        b2 = np.ascontiguousarray(b.reshape(n, k))
+        y = np.zeros((n, k), dt)
+        x = np.zeros((n, k), dt)
+        infos = []
+        fn = emu.chb_front_emu_sweep_f32 if dt == np.float32 else emu.chb_front_emu_sweep_f64
+        for upper in (0, 1):
+            slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+            info = (ctypes.c_int64 * 17)()
+            lib.chb_front_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 17)
+            info = dict(zip(FRONT_INFO_KEYS, list(info)))
+            infos.append(info)
+            w = np.zeros((max(info["n_w_rows"], 1), k), dt)
+            rc = fn(slab, tasks, order, ctypes.c_int(info["n_tasks"]), ctypes.c_int(info["page_bytes"]),
+                    ctypes.c_int(info["tile_rows"]), ctypes.c_int(info["n_warps"]), ctypes.c_int(upper), ctypes.c_int(k), ctypes.c_int(n),
+                    ctypes.c_int64(info["n_w_rows"]), _p(y), _p(w), _p(b2), _p(x))
+            if rc:
+                raise RuntimeError("front schedule interpreter failed with code %d (%s sweep)" % (rc, "backward" if upper else "forward"))
+    finally:
+        lib.chb_front_schedule_destroy(h)
+    return x.reshape(b.shape), infos[0], infos[1]

@@ -74,6 +74,7 @@ def run_one(lib, p, A, perm, cp, ri, v, dt, ks, flags, ctas):
                     e1.record()
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
+                s.check_error()
                 xs = x[:, :2].double().cpu().numpy()
                 bs = b[:, :2].double().cpu().numpy()
                 res = float((np.linalg.norm(A @ xs - bs, axis=0) / np.linalg.norm(bs, axis=0)).max())

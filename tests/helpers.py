@@ -42,6 +42,15 @@ def max_rel_err(x, ref):
     return float((np.abs(x - ref).max(axis=0) / np.abs(ref).max(axis=0)).max())
 
 
+def max_rel_err_elementwise(x, ref, floor=1e-3):
+    """Element-wise error max|x - ref| / max(|ref|, floor * max|ref| of the column) (SURVEY.md 7.3-3 asks for
+    both metrics; the floor keeps entries that are ~0 by cancellation from dominating)."""
+    x = np.asarray(x, np.float64).reshape(len(ref), -1)
+    ref = np.asarray(ref, np.float64).reshape(len(ref), -1)
+    den = np.maximum(np.abs(ref), floor * np.abs(ref).max(axis=0, keepdims=True))
+    return float((np.abs(x - ref) / den).max())
+
+
 def rel_residual(A, x, b):
     x = np.asarray(x, np.float64).reshape(A.shape[0], -1)
     b = np.asarray(b, np.float64).reshape(A.shape[0], -1)

@@ -27,6 +27,7 @@ def _gpu_solve(solver, b):
     xt = torch.zeros_like(bt)
     solver.solve(bt, xt)
     torch.cuda.synchronize()
+    solver.check_error()
     assert np.array_equal(bt.cpu().numpy(), b), "b must not be modified"
     return xt.cpu().numpy()
 
