@@ -90,7 +90,7 @@ struct FrontOptions {
     int fuse_steps = 48;     // a single-panel supernode keeps its below-product in the same task up to this many MMA records
     int split_chunks = 16;   // staged source chunks (of 32 rows) per partial-product task
     int own_chunks = 8;      // trailing staged source chunks a panel task accumulates itself
-    int order_blocks = 24;   // subtree blocks of the ticket order (0: plain level order)
+    int order_blocks = 0;    // subtree blocks of the ticket order (0: plain level order; measured: blocks leave CTAs polling)
 };
 FrontOptions front_options_from_env(int elem);
 

@@ -404,9 +404,18 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
     uint32_t j0 = 0;         // sequence number of the task's first staged record
 
     // waits for staged record sj of the current task; returns its first ring row
+    unsigned long long *t_first_ptr = nullptr, *t_wait_ptr = nullptr;
     auto staged = [&](uint32_t sj) -> int {
         const uint32_t j = j0 + sj;
-        mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
+        if (a.trace && warp == 0) {
+            const unsigned long long c0 = global_ns();
+            mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
+            const unsigned long long c1 = global_ns();
+            *t_wait_ptr += c1 - c0;
+            if (*t_first_ptr == 0) *t_first_ptr = c1;
+        } else {
+            mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
+        }
         return sm.rows_base[j % kRowBars];
     };
     auto store_dst = [&](int perm_row, const V &v) {
@@ -427,7 +436,12 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         const int task = cur.task;
         const uint32_t total = cur.bytes;
         const uint32_t n_pages = (total + page - 1) / page;
-        if (a.trace && leader) a.trace[8 * (size_t) task] = global_ns();
+        unsigned long long t_first_data = 0, t_wait = 0;  // tracing only (warp 0)
+        t_first_ptr = &t_first_data, t_wait_ptr = &t_wait;
+        if (a.trace && leader) {
+            a.trace[8 * (size_t) task] = global_ns();
+            a.trace[8 * (size_t) task + 1] = blockIdx.x;
+        }
         uint32_t n_staged = 0;
 
         // record cursor over the task's pages
@@ -634,7 +648,11 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         // publish: every compute warp's stores of this task are done before the flag is released
         named_barrier(1, NW * 32);
         if (leader) {
-            if (a.trace) a.trace[8 * (size_t) task + 2] = global_ns();
+            if (a.trace) {
+                a.trace[8 * (size_t) task + 2] = global_ns();
+                a.trace[8 * (size_t) task + 3] = t_first_data;
+                a.trace[8 * (size_t) task + 4] = t_wait;
+            }
             st_release_gpu(a.done + task, a.epoch);
             mbar_arrive(sm.tempty + q % kTaskQueue);
         }

@@ -65,7 +65,8 @@ struct FrontArgs {
     Float *wbuf;          // (n_w_rows, round4(k)) update rows / partial products
     const Float *src;     // forward: user's b;  backward: null
     Float *dst;           // backward: user's x;  forward: null
-    unsigned long long *trace;  // optional (debug): 8 words per task {start ns, -, end ns, ...}
+    unsigned long long *trace;  // optional (debug): 8 words per task {start ns, CTA, end ns, first staged rows ready ns,
+                                // ns warp 0 spent waiting for staged rows, -, -, -}
 };
 
 }  // namespace chb
