@@ -31,6 +31,12 @@ public:
         header(type, a, b, c, len);
         return off + 16;
     }
+    // bytes left in the current page of the current task (a record of at most this size starts in this page)
+    size_t room_in_page() const { return m_page - (m_buf.size() - m_task_start) % m_page; }
+    void pad_page() {
+        const size_t in_page = (m_buf.size() - m_task_start) % m_page;
+        if (in_page) header(FR_NOP, 0, 0, 0, m_page - in_page);
+    }
     void put_value(size_t payload_off, size_t index, double v) {
         if (m_elem == 4) {
             const float f = (float) v;  // host-side cast, as reference src/cholesky_solver.cpp:267-270
@@ -424,8 +430,8 @@ struct FrontBuilder {
                 if (below(r) > 0) waits.push_back(owner_task(below_rows(r)[0]));
             sj = emit_loadx(1, loc.c_lo, n_int, 1, loc.ext.data(), n_ext, 0, waits);
         }
-        // sparse rows (same record layout as round 1's REC_LOCAL_ROWS): forward row i of L by ascending column,
-        // backward column j of L by descending row; entries in groups of 4 (zero padding), reciprocal pivots
+        // sparse rows: forward row i of L by ascending column, backward column j of L by descending row; entries in
+        // groups of 4 (zero padding), reciprocal pivots
         struct Entry {
             int idx;
             double v;
@@ -444,42 +450,104 @@ struct FrontBuilder {
             img.n_values += cp[c + 1] - cp[c];
         }
         const int n_rows_total = n_int + n_out;
+        // LEVELS inside the task: a row depends on the rows its entries name; rows of one level are independent and
+        // are dealt to the compute warps (one warp substitutes one row over all RHS columns), a barrier between levels.
+        std::vector<int> level((size_t) n_rows_total, 0);
+        int n_lv = 0;
+        if (!upper) {
+            for (int r = 0; r < n_rows_total; ++r) {
+                int lv = 0;
+                for (const Entry &e : rows[(size_t) r]) lv = std::max(lv, level[(size_t) e.idx] + 1);
+                level[(size_t) r] = lv;
+                n_lv = std::max(n_lv, lv + 1);
+            }
+        } else {
+            for (int r = n_int - 1; r >= 0; --r) {
+                int lv = 0;
+                for (const Entry &e : rows[(size_t) r])
+                    if (e.idx < n_int) lv = std::max(lv, level[(size_t) e.idx] + 1);
+                level[(size_t) r] = lv;
+                n_lv = std::max(n_lv, lv + 1);
+            }
+        }
+        const size_t head_bytes = 2 * (size_t) es;  // {u32 meta, pivot}: pivot at byte es, indices from byte 2 es
         auto row_bytes = [&](int r) {
             const size_t n4 = (rows[(size_t) r].size() + 3) / 4;
-            return 16 + round16(4 * n4) + 4 * n4 * (size_t) es;
+            return round16(head_bytes + 4 * n4) + 4 * n4 * (size_t) es;
         };
-        int j = 0;
-        while (j < n_rows_total) {
-            size_t bytes = 0;
-            int cnt = 0;
-            while (j + cnt < n_rows_total) {
-                const int r = upper ? n_int - 1 - (j + cnt) : j + cnt;
-                if (16 + bytes + row_bytes(r) > (size_t) img.page_bytes) break;
-                bytes += row_bytes(r);
-                cnt += 1;
+        std::vector<std::vector<int>> by_level((size_t) n_lv);
+        for (int r = 0; r < n_rows_total; ++r) by_level[(size_t) level[(size_t) r]].push_back(r);
+        std::vector<std::vector<int>> of_warp((size_t) NW);
+        for (int lv = 0; lv < n_lv; ++lv) {
+            std::vector<int> &rs = by_level[(size_t) lv];
+            std::stable_sort(rs.begin(), rs.end(), [&](int x, int y) { return rows[(size_t) x].size() > rows[(size_t) y].size(); });
+            // longest rows first, each to the least loaded warp
+            size_t load[kFrontMaxWarps] = {0};
+            for (auto &v : of_warp) v.clear();
+            for (int r : rs) {
+                int best = 0;
+                for (int wi = 1; wi < NW; ++wi)
+                    if (load[wi] < load[best]) best = wi;
+                of_warp[(size_t) best].push_back(r);
+                load[best] += rows[(size_t) r].size() / 4 + 2;
             }
-            if (cnt == 0) throw std::logic_error("front schedule: a local row does not fit a page");
-            const size_t off = w.record(FR_LROWS, (uint32_t) cnt, (uint32_t) sj, 0, bytes);
-            size_t at = off;
-            for (int q = 0; q < cnt; ++q) {
-                const int r = upper ? n_int - 1 - (j + q) : j + q;
-                const bool contribution = r >= n_int;  // accumulated from zero, no pivot; stored as +sum (consumers subtract)
-                const std::vector<Entry> &ent = rows[(size_t) r];
-                const size_t n4 = (ent.size() + 3) / 4;
-                if (n4 > 255) throw std::logic_error("front schedule: local row too long");
-                w.put_int(at, 0, (int32_t) ((uint32_t) r | (uint32_t) n4 << 8 | (contribution ? 1u << 16 : 0u)));
-                w.put_value(at + 8, 0, contribution ? -1.0 : 1.0 / diag[(size_t) r]);
-                uint8_t idx[1024];
-                for (size_t i = 0; i < 4 * n4; ++i) idx[i] = (uint8_t) (i < ent.size() ? ent[i].idx : contribution ? 0 : r);
-                w.put_bytes(at + 16, idx, 4 * n4);
-                const size_t voff = at + 16 + round16(4 * n4);
-                for (size_t i = 0; i < ent.size(); ++i) w.put_value(voff, i, ent[i].v);
-                at = voff + 4 * n4 * (size_t) es;
-                img.n_stored_values += (int64_t) (4 * n4) + 1;
+            // records: as many rows as fit the rest of the page / one page, taken evenly from the warps' lists
+            size_t at_w[kFrontMaxWarps] = {0};
+            size_t left = rs.size();
+            while (left > 0) {
+                size_t room = w.room_in_page();
+                if (room < 16 + 48 + 256) room = (size_t) img.page_bytes;
+                room -= 16 + 48;
+                size_t take[kFrontMaxWarps] = {0}, bytes = 0;
+                bool progress = true;
+                while (progress) {
+                    progress = false;
+                    for (int wi = 0; wi < NW; ++wi) {
+                        const size_t q = at_w[wi] + take[wi];
+                        if (q >= of_warp[(size_t) wi].size()) continue;
+                        const size_t rb = row_bytes(of_warp[(size_t) wi][q]);
+                        if (bytes + rb > room) continue;
+                        bytes += rb;
+                        take[wi] += 1;
+                        progress = true;
+                    }
+                }
+                if (bytes == 0) {
+                    if (room + 16 + 48 < (size_t) img.page_bytes) {  // retry on a fresh page
+                        w.pad_page();
+                        continue;
+                    }
+                    throw std::logic_error("front schedule: a local row does not fit a page");
+                }
+                const size_t off = w.record(FR_LROWS, 0, (uint32_t) sj, 0, 48 + bytes);
+                size_t at = off + 48;
+                for (int wi = 0; wi < NW; ++wi) {
+                    w.put_int(off, (size_t) wi, (int32_t) (at - off));
+                    for (size_t q = 0; q < take[wi]; ++q) {
+                        const int r = of_warp[(size_t) wi][at_w[wi] + q];
+                        const bool contribution = r >= n_int;  // accumulated from zero, no pivot; stored as +sum (consumers subtract)
+                        const std::vector<Entry> &ent = rows[(size_t) r];
+                        const size_t n4 = (ent.size() + 3) / 4;
+                        if (n4 > 255) throw std::logic_error("front schedule: local row too long");
+                        w.put_int(at, 0, (int32_t) ((uint32_t) r | (uint32_t) n4 << 8 | (contribution ? 1u << 16 : 0u)));
+                        w.put_value(at + (size_t) es, 0, contribution ? -1.0 : 1.0 / diag[(size_t) r]);
+                        uint8_t idx[1024];
+                        // padding entries (value 0) name the row's first source: a finished, finite row
+                        for (size_t i = 0; i < 4 * n4; ++i) idx[i] = (uint8_t) (i < ent.size() ? ent[i].idx : ent[0].idx);
+                        w.put_bytes(at + head_bytes, idx, 4 * n4);
+                        const size_t voff = at + round16(head_bytes + 4 * n4);
+                        for (size_t i = 0; i < ent.size(); ++i) w.put_value(voff, i, ent[i].v);
+                        at = voff + 4 * n4 * (size_t) es;
+                        img.n_stored_values += (int64_t) (4 * n4) + 1;
+                    }
+                    at_w[wi] += take[wi];
+                    left -= take[wi];
+                }
+                w.put_int(off, (size_t) NW, (int32_t) (at - off));
             }
-            j += cnt;
+            emit_bar();
         }
-        emit_bar();
+        if (n_lv == 0) emit_bar();
         {
             const size_t off = w.record(FR_LSTORE, (uint32_t) n_int | (uint32_t) n_out << 16, (uint32_t) sj, (uint32_t) loc.c_lo,
                                         16 + (upper ? 4 * pad4((size_t) n_int) : 0));
@@ -535,6 +603,32 @@ struct FrontBuilder {
         std::vector<Chunk> src, part;
         std::vector<std::pair<int, int32_t>> entries;
         std::vector<int> done;
+        // Forward, wide supernodes: the right-hand side of every panel is ASSEMBLED AHEAD of the panel chain by a task of
+        // its own (v = b - update rows, parked in the panel's rows of the work vector): the update rows of all the
+        // descendants are then subtracted off the critical path (measured on cfg4: the assembly of a top-separator
+        // panel, thousands of row loads, took 150 us of every 170 us chain step).
+        std::vector<int> assembly_task;
+        if (!upper && np > 1) {
+            for (int pi = 0; pi < np; ++pi) {
+                const int p0 = c0 + pi * P, p1 = std::min(p0 + P, c0 + wd), pw = p1 - p0;
+                entries.clear();
+                for (int r = 0; r < pw; ++r) {
+                    std::vector<int32_t> &lst = contrib[(size_t) dense_row[(size_t) (p0 + r)]];
+                    for (int32_t wr : lst) entries.push_back({r, wr});
+                    std::vector<int32_t>().swap(lst);
+                }
+                open_task(s);
+                img.n_dense_tasks += 1;
+                const int sj = emit_loadx(0, 0, 0, 2, &L.perm[(size_t) p0], pw, 0, child_waits);
+                emit_asm(sj, 0, entries);
+                emit_bar();
+                const size_t off = w.record(FR_LSTORE, (uint32_t) pw, (uint32_t) sj, (uint32_t) p0, 16);
+                w.put_int(off, 0, 0);
+                emit_rel(sj);
+                assembly_task.push_back(cur);
+                close_task();
+            }
+        }
         for (int step = 0; step < np; ++step) {
             const int pi = upper ? np - 1 - step : step;
             const int p0 = c0 + pi * P, p1 = std::min(p0 + P, c0 + wd), pw = p1 - p0;
@@ -567,9 +661,11 @@ struct FrontBuilder {
             emit_accumulate(s, p0, pw, part, true);
             std::vector<int> waits(part_tasks);
             int sjb;
-            if (!upper) {
-                if (step == 0) waits.insert(waits.end(), child_waits.begin(), child_waits.end());
-                else waits.push_back(panel_task[(size_t) s][(size_t) (pi - 1)]);
+            if (!upper && np > 1) {
+                waits.push_back(assembly_task[(size_t) pi]);
+                sjb = emit_loadx(1, p0, pw, 0, nullptr, 0, 0, waits);
+            } else if (!upper) {
+                waits.insert(waits.end(), child_waits.begin(), child_waits.end());
                 sjb = emit_loadx(0, 0, 0, 2, &L.perm[(size_t) p0], pw, 0, waits);
                 for (int r = 0; r < pw; ++r) {
                     std::vector<int32_t> &lst = contrib[(size_t) dense_row[(size_t) (p0 + r)]];

@@ -69,7 +69,10 @@ enum FrontRecord : uint32_t {
     FR_ASM = 4,
     FR_BAR = 5,   // barrier of the compute warps
     FR_REL = 6,   // a = sj: the compute warps are done with that staged record
-    // a = n_rows, b = sj.  payload: sparse rows (panel_schedule.h: REC_LOCAL_ROWS layout, reciprocal pivots).
+    // b = sj.  Sparse rows of ONE dependency level of a local task, dealt to the compute warps.  payload: seg[n_warps + 1]
+    // (byte range of each warp's rows, relative to the payload; padded to 12 ints), then per row: {u32 local row |
+    // n4 << 8 | contribution << 16, pivot at byte elem}, 4 n4 local source indices (u8) from byte 2 elem, padded to 16
+    // bytes, 4 n4 values:  local[row] = ((contribution ? 0 : local[row]) - sum values[i] local[idx[i]]) * pivot
     FR_LROWS = 7,
     // a = n_int | n_ext << 16, b = sj, c = first Y row.  payload: [0] = first W row (forward), [4..] perm[n_int] (backward)
     FR_LSTORE = 8,

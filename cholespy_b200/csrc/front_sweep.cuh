@@ -23,8 +23,9 @@
 //   * the epilogue (FR_EPI) writes tiles to the work vector / the update-row buffer / the user's x through P',
 //     or back into ring rows; FR_ASM subtracts the update rows addressed to the staged right-hand side
 //     (8 independent row loads in flight per warp); diagonal blocks are applied as explicit inverses (more MMAs);
-//   * LOCAL tasks (complete subtrees): rows staged once, substituted in place as sparse rows, one RHS column per
-//     lane, written back once;
+//   * LOCAL tasks (complete subtrees): rows staged once, substituted in place as sparse rows -- dependency level by
+//     level, the rows of a level dealt to the compute warps, one warp per row over all RHS columns -- and written
+//     back once;
 //   * dependencies: one epoch-valued ready flag per task, st.release.gpu after a barrier of the compute warps;
 //     flags are never cleared (the epoch is the solve counter);
 //   * proxies: rows written with generic stores and later read or overwritten by TMA are ordered with
@@ -561,23 +562,24 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                     type = h.x & 0xff;
                 }
             } else if (type == FR_ASM) {
-                // ring[row] -= W[w_row] for this warp's entries, 8 row loads in flight
+                // ring[row] -= W[w_row] for this warp's entries, 8-16 row loads in flight
                 const int *ip = reinterpret_cast<const int *>(pay);
                 const int lo = ip[warp], hi = ip[warp + 1];
                 if (lo < hi) {
                     F *rows = sm.ring + (size_t) (staged(h.y & 0xffffu) + (int) (h.y >> 16)) * kp + lcol;
                     const int2 *ent = reinterpret_cast<const int2 *>(ip + 12);
-                    for (int e = lo; e < hi; e += 8) {
-                        V vals[8];
-                        int rr[8];
+                    constexpr int kInFlight = 64 / ((int) sizeof(F) * CPL) >= 16 ? 16 : 8;  // row loads in flight (<= 64 registers)
+                    for (int e = lo; e < hi; e += kInFlight) {
+                        V vals[kInFlight];
+                        int rr[kInFlight];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < kInFlight; ++j) {
                             const int2 en = ent[min(e + j, hi - 1)];
                             rr[j] = en.x;
                             vals[j] = ld_global<F, CPL>(a.wbuf + (size_t) en.y * kp + lcol);
                         }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < kInFlight; ++j) {
                             if (e + j < hi && active) {
                                 F *dst = rows + (size_t) rr[j] * kp;
                                 V o = ld_shared<F, CPL>(dst);
@@ -595,19 +597,26 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
             } else if (type == FR_LOADX) {
                 n_staged += 1;
             } else if (type == FR_LROWS) {
-                // sparse rows of a local task, substituted in place, one RHS column per lane
-                const int lc = warp * 32 + lane;
-                if (warp * 32 < kp) {
-                    F *lrow = sm.ring + (size_t) staged(h.z) * kp + (lc < kp ? lc : warp * 32);
-                    const unsigned char *qp = pay;
-                    for (int i = 0; i < (int) h.y; ++i) {
+                // sparse rows of one dependency level of a local task: this warp substitutes its rows in place, over all
+                // RHS columns (CPL per lane)
+                const int *ip = reinterpret_cast<const int *>(pay);
+                const unsigned char *qp = pay + ip[warp], *qend = pay + ip[warp + 1];
+                if (qp < qend) {
+                    F *lrow = sm.ring + (size_t) staged(h.z) * kp + lcol;
+                    while (qp < qend) {
                         const uint32_t meta = *reinterpret_cast<const uint32_t *>(qp);
-                        const F pivot = *reinterpret_cast<const F *>(qp + 8);
+                        const F pivot = *reinterpret_cast<const F *>(qp + sizeof(F));
                         const int n4 = (int) (meta >> 8 & 0xff);
-                        const unsigned char *idx = qp + 16;
-                        const F *val = reinterpret_cast<const F *>(qp + 16 + ((4 * n4 + 15) & ~15));
+                        const unsigned char *idx = qp + 2 * sizeof(F);
+                        const F *val = reinterpret_cast<const F *>(qp + ((2 * sizeof(F) + 4 * n4 + 15) & ~(size_t) 15));
                         F *dst = lrow + (size_t) (meta & 0xff) * kp;
-                        F s = (meta >> 16 & 1) ? F(0) : *dst;
+                        V sv;
+                        if (meta >> 16 & 1) {
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) sv.v[c] = F(0);
+                        } else {
+                            sv = ld_shared<F, CPL>(dst);
+                        }
                         for (int g4 = 0; g4 < n4; ++g4) {
                             const uint32_t i4 = *reinterpret_cast<const uint32_t *>(idx + 4 * g4);
                             F vv[4];
@@ -617,11 +626,17 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
 #pragma unroll
                                 for (int jj = 0; jj < AV; ++jj) vv[j + jj] = v0.v[jj];
                             }
+                            V xs[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) s = fma(-vv[j], lrow[(size_t) (i4 >> (8 * j) & 0xff) * kp], s);
+                            for (int j = 0; j < 4; ++j) xs[j] = ld_shared<F, CPL>(lrow + (size_t) (i4 >> (8 * j) & 0xff) * kp);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int c = 0; c < CPL; ++c) sv.v[c] = fma(-vv[j], xs[j].v[c], sv.v[c]);
                         }
-                        s = s * pivot;
-                        if (lc < kp) *dst = s;
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) sv.v[c] *= pivot;
+                        if (active) st_shared<F, CPL>(dst, sv);
                         qp = reinterpret_cast<const unsigned char *>(val + 4 * n4);
                     }
                 }

@@ -177,26 +177,30 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                     std::vector<F> *st = stage(h[2]);
                     if (!st) return -12;
                     const int rows_avail = (int) (st->size() / (size_t) k);
-                    const uint8_t *q = pay;
-                    for (int i = 0; i < (int) h[1]; ++i) {
-                        uint32_t meta;
-                        std::memcpy(&meta, q, 4);
-                        F pivot;
-                        std::memcpy(&pivot, q + 8, sizeof(F));
-                        const int n4 = (int) (meta >> 8 & 0xff), row = (int) (meta & 0xff);
-                        const bool contribution = (meta >> 16 & 1) != 0;
-                        const uint8_t *idx = q + 16;
-                        const F *val = (const F *) (q + 16 + ((4 * n4 + 15) & ~15));
-                        if (row >= rows_avail) return -12;
-                        for (int c = 0; c < k; ++c) {
-                            F a = contribution ? F(0) : (*st)[(size_t) row * k + c];
-                            for (int e = 0; e < 4 * n4; ++e) {
-                                if ((int) idx[e] >= rows_avail) return -12;
-                                a = fmadd(-val[e], (*st)[(size_t) idx[e] * k + c], a);
+                    const size_t es = sizeof(F);
+                    for (int wi = 0; wi < kWarps; ++wi) {
+                        const uint8_t *q = pay + ipay[wi], *qend = pay + ipay[wi + 1];
+                        if (ipay[wi] < 48 || ipay[wi + 1] < ipay[wi] || (uint32_t) ipay[wi + 1] > len - 16) return -12;
+                        while (q < qend) {
+                            uint32_t meta;
+                            std::memcpy(&meta, q, 4);
+                            F pivot;
+                            std::memcpy(&pivot, q + es, sizeof(F));
+                            const int n4 = (int) (meta >> 8 & 0xff), row = (int) (meta & 0xff);
+                            const bool contribution = (meta >> 16 & 1) != 0;
+                            const uint8_t *idx = q + 2 * es;
+                            const F *val = (const F *) (q + ((2 * es + 4 * n4 + 15) & ~(size_t) 15));
+                            if (row >= rows_avail) return -12;
+                            for (int c = 0; c < k; ++c) {
+                                F a = contribution ? F(0) : (*st)[(size_t) row * k + c];
+                                for (int e = 0; e < 4 * n4; ++e) {
+                                    if ((int) idx[e] >= rows_avail || (int) idx[e] == row) return -12;
+                                    a = fmadd(-val[e], (*st)[(size_t) idx[e] * k + c], a);
+                                }
+                                (*st)[(size_t) row * k + c] = a * pivot;
                             }
-                            (*st)[(size_t) row * k + c] = a * pivot;
+                            q = (const uint8_t *) (val + 4 * n4);
                         }
-                        q = (const uint8_t *) (val + 4 * n4);
                     }
                     break;
                 }
