@@ -470,6 +470,8 @@ struct FrontBuilder {
                 n_lv = std::max(n_lv, lv + 1);
             }
         }
+        img.n_local_levels += n_lv;
+        img.n_local_rows += n_rows_total;
         const size_t head_bytes = 2 * (size_t) es;  // {u32 meta, pivot}: pivot at byte es, indices from byte 2 es
         auto row_bytes = [&](int r) {
             const size_t n4 = (rows[(size_t) r].size() + 3) / 4;

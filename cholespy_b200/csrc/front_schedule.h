@@ -113,6 +113,7 @@ struct FrontImage {
     int64_t n_values = 0;            // factor entries referenced (== nnz(L); diagonal blocks count through their inverse)
     int64_t n_stored_values = 0;     // values in the slab
     int64_t n_local_tasks = 0, n_dense_tasks = 0, n_mma = 0, n_asm_entries = 0;
+    int64_t n_local_levels = 0, n_local_rows = 0;  // dependency levels / sparse rows over all local tasks
 };
 
 // Supernode partition + local tasks shared by both sweeps.

@@ -88,20 +88,23 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // instead of hanging the GPU or killing the context; the host reports it after the sweep (GpuSolver::check_error).
 constexpr unsigned long long kWatchdogNs = 20ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *error_word) {
+    // No suspend-time hint: ptxas turns a hinted try_wait into try + NANOSLEEP(hint) loops, which quantises every wait
+    // to the hint (measured with a 20 us hint: 35 % of all warp samples sat in that NANOSLEEP).  The plain form blocks
+    // in hardware for a short, implementation-defined time and wakes up on the phase flip.
     unsigned long long t0 = 0;
     for (unsigned spins = 0;; ++spins) {
         uint32_t ok;
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) return;
-        if ((spins & 1023u) == 1023u) {
+        if ((spins & 4095u) == 4095u) {
             const unsigned long long now = global_ns();
             if (t0 == 0) t0 = now;
             if (now - t0 > kWatchdogNs || *(volatile int *) error_word != 0) {
@@ -225,37 +228,59 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
     int head = 0;
     uint32_t q = 0;           // tasks queued so far
 
-    // current and next task (warp-uniform copies): descriptor + first global page
-    int t_cur = 0, t_next = 0;
+    // Three tickets are in the loader's hands: the current task, the next one (descriptor known: its slab is
+    // prefetched into L2 and its first pages into the ring while the current task runs) and the one after (ticket
+    // drawn, descriptor load in flight).  Ticket and descriptor round trips are issued one task ahead of their use,
+    // so neither is exposed: per-task loader latency is what bounds the throughput of small tasks.
+    int t_cur = 0, t_next = 0, t_nn = 0;
     SweepTask d_cur{0ull, 0u, 0u}, d_next{0ull, 0u, 0u};
     uint32_t first_cur = 0, first_next = 0;
-    auto fetch = [&](int &t, SweepTask &d) {
-        int tt = 0;
-        unsigned long long off = 0;
-        unsigned int bytes = 0, id = 0;
-        if (lane == 0) {
-            tt = atomicAdd(a.ticket, 1);
-            if (tt < a.n_tasks) {
-                const SweepTask s = a.tasks[tt];
-                off = s.offset, bytes = s.bytes, id = s.level;
-            }
+    bool next_known = false;  // d_next holds the descriptor of t_next (warp-uniform copy)
+    SweepTask s_next{0ull, 0u, 0u};  // lane 0: descriptor load of t_next, possibly still in flight
+    auto draw = [&]() {  // lane 0 only; the value is consumed much later
+        return lane == 0 ? atomicAdd(a.ticket, 1) : 0;
+    };
+    auto load_desc = [&](int t) {
+        SweepTask d{0ull, 0u, 0u};
+        if (lane == 0 && t < a.n_tasks) d = a.tasks[t];
+        return d;
+    };
+    auto broadcast = [&](const SweepTask &d) {
+        SweepTask r;
+        r.offset = __shfl_sync(kFullMask, d.offset, 0);
+        r.bytes = __shfl_sync(kFullMask, d.bytes, 0);
+        r.level = __shfl_sync(kFullMask, d.level, 0);
+        return r;
+    };
+    auto prefetch_l2 = [&](const SweepTask &d) {  // the whole slab of a task (at most 1 MB), 32 KB per lane
+        for (uint32_t off = (uint32_t) lane * 32768u; off < d.bytes && off < (1u << 20); off += 32u * 32768u) {
+            const uint32_t bytes = min(32768u, d.bytes - off);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.slab + d.offset + off), "r"(bytes) : "memory");
         }
-        t = __shfl_sync(kFullMask, tt, 0);
-        d.offset = __shfl_sync(kFullMask, off, 0);
-        d.bytes = __shfl_sync(kFullMask, bytes, 0);
-        d.level = __shfl_sync(kFullMask, id, 0);
     };
     auto pages_of = [&](const SweepTask &d) { return (d.bytes + page - 1) / page; };
+    // the next task's descriptor: made warp-uniform at its first use
+    auto know_next = [&]() {
+        if (next_known) return;
+        d_next = broadcast(s_next);
+        next_known = true;
+        if (t_next < a.n_tasks) prefetch_l2(d_next);
+    };
     // hands pages to TMA in global order while the ring has room; blocks only for page `must` (the one needed now)
     auto feed_pages = [&](uint32_t must) {
         for (;;) {
+            if (issued >= must + kStages) break;
             // which task owns page `issued`?
             const SweepTask *d;
             uint32_t first;
-            if (issued < first_cur + pages_of(d_cur)) d = &d_cur, first = first_cur;
-            else if (t_next < a.n_tasks && issued < first_next + pages_of(d_next)) d = &d_next, first = first_next;
-            else break;
-            if (issued >= must + kStages) break;
+            if (issued < first_cur + pages_of(d_cur)) {
+                d = &d_cur, first = first_cur;
+            } else {
+                if (t_next >= a.n_tasks) break;
+                know_next();
+                if (issued >= first_next + pages_of(d_next)) break;
+                d = &d_next, first = first_next;
+            }
             const uint32_t st = issued % kStages, fill = issued / kStages;
             if (fill > 0) {
                 if (issued <= must) {
@@ -275,7 +300,10 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
         }
     };
 
-    fetch(t_cur, d_cur);
+    t_cur = __shfl_sync(kFullMask, draw(), 0);
+    d_cur = broadcast(load_desc(t_cur));
+    if (t_cur < a.n_tasks) prefetch_l2(d_cur);
+    t_next = __shfl_sync(kFullMask, draw(), 0);
     first_cur = 0;
     for (;;) {
         if (t_cur >= a.n_tasks) {
@@ -287,9 +315,11 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
             break;
         }
         const uint32_t n_pages = pages_of(d_cur);
-        // the next ticket is drawn now: its descriptor round trip and first pages overlap this task
-        fetch(t_next, d_next);
         first_next = first_cur + n_pages;
+        // in flight from here on, consumed later: the next task's descriptor and the ticket after it
+        s_next = load_desc(t_next);
+        next_known = false;
+        t_nn = draw();
         if (lane == 0) {
             if (q >= kTaskQueue) mbar_wait(sm.tempty + q % kTaskQueue, ((q / kTaskQueue) - 1) & 1, a.error);
             sm.queue[q % kTaskQueue] = QueuedTask{t_cur, (int) d_cur.level, d_cur.bytes, 0u};
@@ -318,6 +348,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
                     unsigned spins = 0;
                     unsigned long long t0 = 0;
                     while (ld_acquire_gpu(flag) != epoch) {
+                        __nanosleep(100);  // thousands of loaders poll: keep their acquire loads (each invalidates L1) off the L2 queues
                         if ((++spins & 4095u) == 0) {
                             const unsigned long long now = global_ns();
                             if (t0 == 0) t0 = now;
@@ -380,10 +411,11 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
             if (lane == 0) mbar_arrive(sm.empty + stage);
         }
         // next task becomes current
+        know_next();
         t_cur = t_next;
         d_cur = d_next;
         first_cur = first_next;
-        t_next = a.n_tasks;
+        t_next = __shfl_sync(kFullMask, t_nn, 0);
     }
 }
 
@@ -400,6 +432,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
     const int lcol = active ? col : 0;           // a column this lane may always read
     const bool leader = warp == 0 && lane == 0;
     const bool dst_vec = a.dst_vec != 0;
+    const int dbg = a.debug;
 
     uint32_t gpage = 0;      // global index of the current task's first page
     uint32_t j0 = 0;         // sequence number of the task's first staged record
@@ -491,7 +524,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                 for (;;) {
                     if (type == FR_MMA) {
                         const int t = warp - (int) (h.y & 255u);
-                        if (t >= 0 && t < (int) (h.y >> 8 & 255u)) {
+                        if (t >= 0 && t < (int) (h.y >> 8 & 255u) && !(dbg & 8)) {
                             const int n_src = (int) (h.y >> 16 & 255u);
                             const int base = staged(h.z & 0xffffu) + (int) (h.z >> 16);
                             if (h.y >> 24 & 1u) {
@@ -523,7 +556,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                     } else if (type == FR_EPI) {
                         const int t = warp - (int) (h.y & 255u);
                         const uint32_t mode = h.y >> 16;
-                        if (t >= 0 && t < (int) (h.y >> 8 & 255u)) {
+                        if (t >= 0 && t < (int) (h.y >> 8 & 255u) && !(dbg & 32)) {
                             const int r0 = t * TR;
                             const int nvalid = min(TR, (int) (h.z & 0xffffu) - r0);
                             const int *ip = reinterpret_cast<const int *>(pay);
@@ -556,7 +589,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                     } else if (type == FR_LOADX) {
                         n_staged += 1;
                     } else if (type == FR_BAR) {
-                        named_barrier(1, NW * 32);
+                        if (!(dbg & 4)) named_barrier(1, NW * 32);
                     }
                     if (!next_record(h, pay)) break;  // (malformed stream: an accumulation without epilogue)
                     type = h.x & 0xff;
@@ -565,7 +598,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                 // ring[row] -= W[w_row] for this warp's entries, 8-16 row loads in flight
                 const int *ip = reinterpret_cast<const int *>(pay);
                 const int lo = ip[warp], hi = ip[warp + 1];
-                if (lo < hi) {
+                if (lo < hi && !(dbg & 16)) {
                     F *rows = sm.ring + (size_t) (staged(h.y & 0xffffu) + (int) (h.y >> 16)) * kp + lcol;
                     const int2 *ent = reinterpret_cast<const int2 *>(ip + 12);
                     constexpr int kInFlight = 64 / ((int) sizeof(F) * CPL) >= 16 ? 16 : 8;  // row loads in flight (<= 64 registers)
@@ -591,12 +624,12 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                     }
                 }
             } else if (type == FR_BAR) {
-                named_barrier(1, NW * 32);
+                if (!(dbg & 4)) named_barrier(1, NW * 32);
             } else if (type == FR_REL) {
                 release(h.y);
             } else if (type == FR_LOADX) {
                 n_staged += 1;
-            } else if (type == FR_LROWS) {
+            } else if (type == FR_LROWS && !(dbg & 1)) {
                 // sparse rows of one dependency level of a local task: this warp substitutes its rows in place, over all
                 // RHS columns (CPL per lane)
                 const int *ip = reinterpret_cast<const int *>(pay);
@@ -617,18 +650,29 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                         } else {
                             sv = ld_shared<F, CPL>(dst);
                         }
+                        // the next group's indices and values are fetched while this group's source rows are in flight
+                        uint32_t i4n = 0;
+                        Vec<F, AV> vn[4 / AV];
+                        if (n4 > 0) {
+                            i4n = *reinterpret_cast<const uint32_t *>(idx);
+#pragma unroll
+                            for (int j = 0; j < 4 / AV; ++j) vn[j] = ld_shared<F, AV>(val + j * AV);
+                        }
                         for (int g4 = 0; g4 < n4; ++g4) {
-                            const uint32_t i4 = *reinterpret_cast<const uint32_t *>(idx + 4 * g4);
+                            const uint32_t i4 = i4n;
                             F vv[4];
 #pragma unroll
-                            for (int j = 0; j < 4; j += AV) {
-                                const Vec<F, AV> v0 = ld_shared<F, AV>(val + 4 * g4 + j);
+                            for (int j = 0; j < 4 / AV; ++j)
 #pragma unroll
-                                for (int jj = 0; jj < AV; ++jj) vv[j + jj] = v0.v[jj];
-                            }
+                                for (int jj = 0; jj < AV; ++jj) vv[j * AV + jj] = vn[j].v[jj];
                             V xs[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) xs[j] = ld_shared<F, CPL>(lrow + (size_t) (i4 >> (8 * j) & 0xff) * kp);
+                            if (g4 + 1 < n4) {
+                                i4n = *reinterpret_cast<const uint32_t *>(idx + 4 * (g4 + 1));
+#pragma unroll
+                                for (int j = 0; j < 4 / AV; ++j) vn[j] = ld_shared<F, AV>(val + 4 * (g4 + 1) + j * AV);
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -640,7 +684,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                         qp = reinterpret_cast<const unsigned char *>(val + 4 * n4);
                     }
                 }
-            } else if (type == FR_LSTORE) {
+            } else if (type == FR_LSTORE && !(dbg & 2)) {
                 const int n_int = (int) (h.y & 0xffffu), n_ext = (int) (h.y >> 16);
                 const int *ip = reinterpret_cast<const int *>(pay);
                 const F *rows = sm.ring + (size_t) staged(h.z) * kp + lcol;

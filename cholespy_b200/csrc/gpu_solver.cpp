@@ -508,6 +508,8 @@ void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst) {
         a.page_bytes = s.page_bytes;
         a.src_tma = (((uintptr_t) src & 15) == 0 && ((size_t) k * (size_t) m_elem) % 16 == 0) ? 1 : 0;
         a.dst_vec = (((uintptr_t) dst & 15) == 0 && k % 4 == 0) ? 1 : 0;
+        a.debug = 0;
+        if (const char *v = std::getenv("CHB_FRONT_DEBUG")) a.debug = std::atoi(v);
         a.slab = (const unsigned char *) s.slab;
         a.tasks = (const SweepTask *) s.tasks;
         a.done = (int *) s.done;

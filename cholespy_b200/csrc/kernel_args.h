@@ -55,6 +55,7 @@ struct FrontArgs {
     int page_bytes;       // slab page size (front_schedule.h: front_page_bytes)
     int src_tma;          // rows of the user's b can be fetched by TMA (16-byte aligned, 16-byte multiples)
     int dst_vec;          // rows of the user's x can be written with vector stores
+    int debug;            // timing experiments only (CHB_FRONT_DEBUG): bits skip LROWS / LSTORE / BAR / MMA / ASM / EPI bodies (results invalid)
     const unsigned char *slab;
     const SweepTask *tasks;     // ticket-ordered; `level` = task id = index of its ready flag
     int *done;            // per-task epoch flags

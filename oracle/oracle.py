@@ -242,7 +242,7 @@ _front_emu = None
 
 FRONT_INFO_KEYS = ("n_tasks", "slab_bytes", "page_bytes", "tile_rows", "n_w_rows", "max_stage_rows", "n_levels", "n_values",
                    "n_stored_values", "n_local_tasks", "n_dense_tasks", "n_mma", "n_asm_entries", "n_supernodes", "n_locals",
-                   "n_blocks", "n_warps")
+                   "n_blocks", "n_warps", "n_local_levels", "n_local_rows")
 
 
 def _load_front_emu():
@@ -279,8 +279,8 @@ def front_schedule_solve(lib, l_colptr, l_rowidx, l_vals, perm, b):
         fn = emu.chb_front_emu_sweep_f32 if dt == np.float32 else emu.chb_front_emu_sweep_f64
         for upper in (0, 1):
             slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-            info = (ctypes.c_int64 * 17)()
-            lib.chb_front_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 17)
+            info = (ctypes.c_int64 * 19)()
+            lib.chb_front_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 19)
             info = dict(zip(FRONT_INFO_KEYS, list(info)))
             infos.append(info)
             w = np.zeros((max(info["n_w_rows"], 1), k), dt)

@@ -32,8 +32,8 @@ def main():
     es = 4 if dt == "f" else 8
     for upper in (0, 1):
         slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-        info = (ctypes.c_int64 * 17)()
-        lib.chb_front_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 17)
+        info = (ctypes.c_int64 * 19)()
+        lib.chb_front_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 19)
         info = dict(zip(FRONT_INFO_KEYS, list(info)))
         nt = info["n_tasks"]
         td = np.ctypeslib.as_array(ctypes.cast(tasks, ctypes.POINTER(ctypes.c_uint32)), shape=(nt, 4))

@@ -55,8 +55,8 @@ def main():
         assert got == buf.size, (got, buf.size)
         tr = buf.reshape(nt, 8).astype(np.int64)
         slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-        sinfo = (ctypes.c_int64 * 17)()
-        lib.chb_front_schedule_sweep(hs, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), sinfo, 17)
+        sinfo = (ctypes.c_int64 * 19)()
+        lib.chb_front_schedule_sweep(hs, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), sinfo, 19)
         assert int(sinfo[0]) == nt
         td = np.ctypeslib.as_array(ctypes.cast(tasks, ctypes.POINTER(ctypes.c_uint32)), shape=(nt, 4)).copy()
         od = np.ctypeslib.as_array(ctypes.cast(order, ctypes.POINTER(ctypes.c_int32)), shape=(nt,)).copy()
