@@ -21,18 +21,40 @@ public:
     Writer(std::vector<uint8_t> &buf, int page, int elem) : m_buf(buf), m_page((size_t) page), m_elem(elem) {}
     void begin_task() { m_task_start = m_buf.size(); }
     size_t size() const { return m_buf.size(); }
-    // Reserves a zero-filled record; returns the byte offset of its payload.
+    // Reserves a zero-filled record; returns the byte offset of its payload.  Every page starts with a DIRECTORY record
+    // listing the page's staged (FR_LOADX) records, so that the loader warp jumps to them instead of walking every record.
     size_t record(uint32_t type, uint32_t a, uint32_t b, uint32_t c, size_t payload_bytes) {
         const size_t len = 16 + round16(payload_bytes);
-        if (len > m_page) throw std::logic_error("front schedule: record larger than a page");
-        const size_t in_page = (m_buf.size() - m_task_start) % m_page;
-        if (in_page + len > m_page) header(FR_NOP, 0, 0, 0, m_page - in_page);
+        if (len > m_page - 16) throw std::logic_error("front schedule: record larger than a page");
+        size_t in_page = (m_buf.size() - m_task_start) % m_page;
+        if (in_page != 0 && in_page + len > m_page) {
+            header(FR_NOP, 0, 0, 0, m_page - in_page);
+            in_page = 0;
+        }
+        if (in_page == 0) start_page();
         const size_t off = m_buf.size();
         header(type, a, b, c, len);
+        if (type == FR_LOADX) {
+            uint32_t h0;
+            std::memcpy(&h0, &m_buf[m_dir], 4);
+            const uint32_t cnt = h0 >> 24;
+            if (cnt < 6) {
+                const uint16_t units = (uint16_t) ((off - m_dir) / 16);
+                std::memcpy(&m_buf[m_dir + 4 + 2 * cnt], &units, 2);
+                h0 += 1u << 24;
+            } else {
+                h0 = (h0 & 0x00ffffffu) | 7u << 24;  // more than six: the loader walks the page
+            }
+            std::memcpy(&m_buf[m_dir], &h0, 4);
+        }
         return off + 16;
     }
-    // bytes left in the current page of the current task (a record of at most this size starts in this page)
-    size_t room_in_page() const { return m_page - (m_buf.size() - m_task_start) % m_page; }
+    // bytes a record may still take in the current page of the current task
+    size_t room_in_page() const {
+        const size_t in_page = (m_buf.size() - m_task_start) % m_page;
+        return in_page == 0 ? m_page - 16 : m_page - in_page;
+    }
+    size_t page_overhead() const { return 16; }
     void pad_page() {
         const size_t in_page = (m_buf.size() - m_task_start) % m_page;
         if (in_page) header(FR_NOP, 0, 0, 0, m_page - in_page);
@@ -49,6 +71,10 @@ public:
     void put_bytes(size_t payload_off, const void *src, size_t n) { std::memcpy(&m_buf[payload_off], src, n); }
 
 private:
+    void start_page() {
+        m_dir = m_buf.size();
+        header(FR_DIR, 0, 0, 0, 16);
+    }
     void header(uint32_t type, uint32_t a, uint32_t b, uint32_t c, size_t len) {
         const size_t off = m_buf.size();
         m_buf.resize(off + len);  // zero-filled
@@ -59,6 +85,7 @@ private:
     size_t m_page;
     int m_elem;
     size_t m_task_start = 0;
+    size_t m_dir = 0;  // offset of the current page's directory record
 };
 
 int env_int(const char *name, int dflt) {
@@ -281,7 +308,7 @@ struct FrontBuilder {
         std::stable_sort(entries.begin(), entries.end(), [nw](const std::pair<int, int32_t> &x, const std::pair<int, int32_t> &y) {
             return (x.first % nw) != (y.first % nw) ? (x.first % nw) < (y.first % nw) : x.first < y.first;
         });
-        const size_t cap = ((size_t) img.page_bytes - 16 - 48) / 8;
+        const size_t cap = ((size_t) img.page_bytes - 16 - 16 - 48) / 8;
         // a record holds complete rows only (a row's entries must be applied by one warp in one go is not required, but
         // keeping per-warp segments sorted is): simply cut the per-warp lists proportionally
         std::vector<size_t> seg_lo((size_t) NW + 1, 0);
@@ -450,57 +477,108 @@ struct FrontBuilder {
             img.n_values += cp[c + 1] - cp[c];
         }
         const int n_rows_total = n_int + n_out;
-        // LEVELS inside the task: a row depends on the rows its entries name; rows of one level are independent and
-        // are dealt to the compute warps (one warp substitutes one row over all RHS columns), a barrier between levels.
-        std::vector<int> level((size_t) n_rows_total, 0);
+        // Dealing the rows to the compute warps (one warp substitutes one row over all RHS columns).
+        //   * SUBTREES: the task's rows form a forest (its elimination trees); subtrees of about 1/n_warps of the work are
+        //     given whole to one warp, which substitutes their rows one after the other -- a row depends only on rows of
+        //     its own subtree (forward: descendants, done before; backward: ancestors, see below), so this phase needs no
+        //     synchronisation at all;
+        //   * what is left -- the few rows ABOVE those subtrees, and (forward) the contribution rows, which collect
+        //     from several subtrees -- is done level by level, the rows of a level dealt to the warps, a barrier between
+        //     levels.  Forward: subtrees, barrier, upper levels.  Backward: upper levels, then the subtrees.
+        std::vector<int> lparent((size_t) n_int, -1);
+        for (int j = 0; j < n_int; ++j) {
+            const int c = loc.c_lo + j;
+            if (cp[c + 1] - cp[c] > 1 && ri[cp[c] + 1] < loc.c_hi) lparent[(size_t) j] = ri[cp[c] + 1] - loc.c_lo;
+        }
+        auto cost_of = [&](int r) { return (int64_t) rows[(size_t) r].size() / 4 + 2; };
+        std::vector<int64_t> sub_w((size_t) n_int);
+        int64_t total_w = 0;
+        for (int j = 0; j < n_int; ++j) sub_w[(size_t) j] = cost_of(j), total_w += cost_of(j);
+        for (int j = 0; j < n_int; ++j)
+            if (lparent[(size_t) j] >= 0) sub_w[(size_t) lparent[(size_t) j]] += sub_w[(size_t) j];
+        const int64_t target = std::max<int64_t>(total_w / NW + 1, 12);
+        std::vector<int> group((size_t) n_int, -1);  // warp subtree of a row, or -1: upper row
+        std::vector<int64_t> group_w;
+        for (int j = n_int - 1; j >= 0; --j) {
+            const int q = lparent[(size_t) j];
+            if (q >= 0 && group[(size_t) q] >= 0) {
+                group[(size_t) j] = group[(size_t) q];
+            } else if (sub_w[(size_t) j] <= target) {
+                group[(size_t) j] = (int) group_w.size();
+                group_w.push_back(sub_w[(size_t) j]);
+            }
+        }
+        std::vector<int> warp_of_group(group_w.size());
+        {
+            std::vector<int> by_w(group_w.size());
+            std::iota(by_w.begin(), by_w.end(), 0);
+            std::stable_sort(by_w.begin(), by_w.end(), [&](int x, int y) { return group_w[(size_t) x] > group_w[(size_t) y]; });
+            int64_t load[kFrontMaxWarps] = {0};
+            for (int gi : by_w) {
+                int best = 0;
+                for (int wi = 1; wi < NW; ++wi)
+                    if (load[wi] < load[best]) best = wi;
+                warp_of_group[(size_t) gi] = best;
+                load[best] += group_w[(size_t) gi];
+            }
+        }
+        // levels among the upper INTERNAL rows (dependencies on subtree rows are covered by the phase order); the
+        // contribution rows (forward) depend on internal rows only and form one last phase
+        std::vector<int> level((size_t) n_rows_total, -1);
         int n_lv = 0;
+        auto is_upper = [&](int r) { return r < n_int && group[(size_t) r] < 0; };
         if (!upper) {
-            for (int r = 0; r < n_rows_total; ++r) {
+            for (int r = 0; r < n_int; ++r) {
+                if (!is_upper(r)) continue;
                 int lv = 0;
-                for (const Entry &e : rows[(size_t) r]) lv = std::max(lv, level[(size_t) e.idx] + 1);
+                for (const Entry &e : rows[(size_t) r])
+                    if (is_upper(e.idx)) lv = std::max(lv, level[(size_t) e.idx] + 1);
                 level[(size_t) r] = lv;
                 n_lv = std::max(n_lv, lv + 1);
             }
         } else {
             for (int r = n_int - 1; r >= 0; --r) {
+                if (!is_upper(r)) continue;
                 int lv = 0;
                 for (const Entry &e : rows[(size_t) r])
-                    if (e.idx < n_int) lv = std::max(lv, level[(size_t) e.idx] + 1);
+                    if (e.idx < n_int && is_upper(e.idx)) lv = std::max(lv, level[(size_t) e.idx] + 1);
                 level[(size_t) r] = lv;
                 n_lv = std::max(n_lv, lv + 1);
             }
         }
-        img.n_local_levels += n_lv;
+        // level by level (a barrier each, ~8 cost units) or all upper rows one after the other on one warp?
+        bool upper_serial = false;
+        {
+            std::vector<int64_t> lv_max((size_t) n_lv, 0);
+            int64_t serial = 0;
+            for (int r = 0; r < n_int; ++r)
+                if (level[(size_t) r] >= 0) {
+                    serial += cost_of(r);
+                    lv_max[(size_t) level[(size_t) r]] = std::max(lv_max[(size_t) level[(size_t) r]], cost_of(r));
+                }
+            int64_t leveled = 0;
+            for (int64_t v : lv_max) leveled += v + 8;
+            upper_serial = serial <= leveled;
+        }
+        img.n_local_levels += (upper_serial ? (n_lv > 0 ? 1 : 0) : n_lv) + 1 + (n_out > 0 ? 1 : 0);
         img.n_local_rows += n_rows_total;
         const size_t head_bytes = 2 * (size_t) es;  // {u32 meta, pivot}: pivot at byte es, indices from byte 2 es
         auto row_bytes = [&](int r) {
             const size_t n4 = (rows[(size_t) r].size() + 3) / 4;
             return round16(head_bytes + 4 * n4) + 4 * n4 * (size_t) es;
         };
-        std::vector<std::vector<int>> by_level((size_t) n_lv);
-        for (int r = 0; r < n_rows_total; ++r) by_level[(size_t) level[(size_t) r]].push_back(r);
         std::vector<std::vector<int>> of_warp((size_t) NW);
-        for (int lv = 0; lv < n_lv; ++lv) {
-            std::vector<int> &rs = by_level[(size_t) lv];
-            std::stable_sort(rs.begin(), rs.end(), [&](int x, int y) { return rows[(size_t) x].size() > rows[(size_t) y].size(); });
-            // longest rows first, each to the least loaded warp
-            size_t load[kFrontMaxWarps] = {0};
-            for (auto &v : of_warp) v.clear();
-            for (int r : rs) {
-                int best = 0;
-                for (int wi = 1; wi < NW; ++wi)
-                    if (load[wi] < load[best]) best = wi;
-                of_warp[(size_t) best].push_back(r);
-                load[best] += rows[(size_t) r].size() / 4 + 2;
-            }
-            // records: as many rows as fit the rest of the page / one page, taken evenly from the warps' lists
+        // one phase: every warp substitutes its list in order; records as large as the pages allow; then a barrier
+        auto emit_phase = [&]() {
             size_t at_w[kFrontMaxWarps] = {0};
-            size_t left = rs.size();
+            size_t left = 0;
+            for (const auto &v : of_warp) left += v.size();
             while (left > 0) {
                 size_t room = w.room_in_page();
-                if (room < 16 + 48 + 256) room = (size_t) img.page_bytes;
+                if (room < 16 + 48 + 256) room = (size_t) img.page_bytes - w.page_overhead();
                 room -= 16 + 48;
                 size_t take[kFrontMaxWarps] = {0}, bytes = 0;
+                // rows are taken evenly from the warps' lists, keeping each list's order
                 bool progress = true;
                 while (progress) {
                     progress = false;
@@ -515,7 +593,7 @@ struct FrontBuilder {
                     }
                 }
                 if (bytes == 0) {
-                    if (room + 16 + 48 < (size_t) img.page_bytes) {  // retry on a fresh page
+                    if (room + 16 + 48 < (size_t) img.page_bytes - w.page_overhead()) {  // retry on a fresh page
                         w.pad_page();
                         continue;
                     }
@@ -548,8 +626,68 @@ struct FrontBuilder {
                 w.put_int(off, (size_t) NW, (int32_t) (at - off));
             }
             emit_bar();
+        };
+        auto subtree_phase = [&]() {
+            for (auto &v : of_warp) v.clear();
+            for (int q = 0; q < n_int; ++q) {
+                const int r = upper ? n_int - 1 - q : q;
+                if (group[(size_t) r] >= 0) of_warp[(size_t) warp_of_group[(size_t) group[(size_t) r]]].push_back(r);
+            }
+            emit_phase();
+        };
+        auto upper_phases = [&]() {
+            if (n_lv == 0) return;
+            if (upper_serial) {
+                for (auto &v : of_warp) v.clear();
+                for (int q = 0; q < n_int; ++q) {
+                    const int r = upper ? n_int - 1 - q : q;
+                    if (level[(size_t) r] >= 0) of_warp[0].push_back(r);
+                }
+                emit_phase();
+                return;
+            }
+            std::vector<std::vector<int>> by_level((size_t) n_lv);
+            for (int r = 0; r < n_int; ++r)
+                if (level[(size_t) r] >= 0) by_level[(size_t) level[(size_t) r]].push_back(r);
+            for (int lv = 0; lv < n_lv; ++lv) {
+                std::vector<int> &rs = by_level[(size_t) lv];
+                std::stable_sort(rs.begin(), rs.end(), [&](int x, int y) { return rows[(size_t) x].size() > rows[(size_t) y].size(); });
+                int64_t load[kFrontMaxWarps] = {0};
+                for (auto &v : of_warp) v.clear();
+                for (int r : rs) {  // longest rows first, each to the least loaded warp
+                    int best = 0;
+                    for (int wi = 1; wi < NW; ++wi)
+                        if (load[wi] < load[best]) best = wi;
+                    of_warp[(size_t) best].push_back(r);
+                    load[best] += cost_of(r);
+                }
+                emit_phase();
+            }
+        };
+        auto contribution_phase = [&]() {
+            if (n_out == 0) return;
+            std::vector<int> rs;
+            for (int r = n_int; r < n_rows_total; ++r) rs.push_back(r);
+            std::stable_sort(rs.begin(), rs.end(), [&](int x, int y) { return rows[(size_t) x].size() > rows[(size_t) y].size(); });
+            int64_t load[kFrontMaxWarps] = {0};
+            for (auto &v : of_warp) v.clear();
+            for (int r : rs) {
+                int best = 0;
+                for (int wi = 1; wi < NW; ++wi)
+                    if (load[wi] < load[best]) best = wi;
+                of_warp[(size_t) best].push_back(r);
+                load[best] += cost_of(r);
+            }
+            emit_phase();
+        };
+        if (!upper) {
+            subtree_phase();
+            upper_phases();
+            contribution_phase();
+        } else {
+            upper_phases();
+            subtree_phase();
         }
-        if (n_lv == 0) emit_bar();
         {
             const size_t off = w.record(FR_LSTORE, (uint32_t) n_int | (uint32_t) n_out << 16, (uint32_t) sj, (uint32_t) loc.c_lo,
                                         16 + (upper ? 4 * pad4((size_t) n_int) : 0));

@@ -30,7 +30,7 @@
 //   * tickets are ordered subtree block by subtree block (level order inside a block), so update rows
 //     are consumed while still L2-resident.
 //
-// Record stream ("slab") of a task: 16-byte header {type | len16 << 8, a, b, c} + payload, no record
+// Record stream ("slab") of a task: 16-byte header {type | len16 << 8 (16 bits), a, b, c} + payload, no record
 // straddles a page (page_bytes).  STAGED records (FR_LOADX) are executed by the CTA's loader warp: wait
 // for producer flags, copy rows into the shared-memory row ring with TMA; all other records by the compute
 // warps.  Staged records are numbered 0, 1, ... inside a task (`sj`) and released in that order.
@@ -76,6 +76,9 @@ enum FrontRecord : uint32_t {
     FR_LROWS = 7,
     // a = n_int | n_ext << 16, b = sj, c = first Y row.  payload: [0] = first W row (forward), [4..] perm[n_int] (backward)
     FR_LSTORE = 8,
+    // First record of every page (16 bytes): bits 24-31 of the header word = number of FR_LOADX records in the page
+    // (7: more than six, walk the page), then six u16 offsets of those records, in 16-byte units from the page start.
+    FR_DIR = 9,
 };
 enum FrontEpiMode : uint32_t {
     FE_RING_SUB = 1,  // ring[row] -= acc

@@ -46,7 +46,7 @@ constexpr int kRowBars = 16;     // staged records in flight
 constexpr int kTaskQueue = 4;    // task descriptors the loader may run ahead
 constexpr unsigned kFullMask = 0xffffffffu;
 
-enum : uint32_t { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE };
+enum : uint32_t { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE, FR_DIR };
 enum : uint32_t { FE_RING_SUB = 1, FE_RING_SET = 2, FE_Y = 4, FE_W = 8, FE_DST = 16 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -65,6 +65,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS); completion is reported to an mbarrier by cp_async_arrive.
+// Used for GATHERED rows: one warp-wide instruction moves a 512-byte row, where a bulk copy per row costs a TMA
+// request each (measured: ~50 ns per row, the fixed cost of a local task's 112-row right-hand side).
+__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+// The mbarrier's pending count is incremented now and decremented when all prior cp.async of this thread are done.
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -227,6 +237,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
     int rows_in_flight = 0;
     int head = 0;
     uint32_t q = 0;           // tasks queued so far
+    int seen0 = -1, seen1 = -1;  // flags known to be set (this epoch)
 
     // Three tickets are in the loader's hands: the current task, the next one (descriptor known: its slab is
     // prefetched into L2 and its first pages into the ring while the current task runs) and the one after (ticket
@@ -264,7 +275,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
         if (next_known) return;
         d_next = broadcast(s_next);
         next_known = true;
-        if (t_next < a.n_tasks) prefetch_l2(d_next);
+        if (t_next < a.n_tasks && (a.debug & 64)) prefetch_l2(d_next);
     };
     // hands pages to TMA in global order while the ring has room; blocks only for page `must` (the one needed now)
     auto feed_pages = [&](uint32_t must) {
@@ -302,7 +313,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
 
     t_cur = __shfl_sync(kFullMask, draw(), 0);
     d_cur = broadcast(load_desc(t_cur));
-    if (t_cur < a.n_tasks) prefetch_l2(d_cur);
+    if (t_cur < a.n_tasks && (a.debug & 64)) prefetch_l2(d_cur);
     t_next = __shfl_sync(kFullMask, draw(), 0);
     first_cur = 0;
     for (;;) {
@@ -326,42 +337,78 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
             mbar_arrive(sm.tfull + q % kTaskQueue);
         }
         q += 1;
+        bool traced_first = false;
+        const int tsel = (a.debug >> 8) & 3;  // which three loader events go to trace words 5..7
+        auto stamp = [&](int sel, int word) {
+            if (a.trace && lane == 0 && tsel == sel) a.trace[8 * (size_t) d_cur.level + word] = global_ns();
+        };
+        stamp(0, 5);
+        stamp(1, 5);
         for (uint32_t pg = 0; pg < n_pages; ++pg) {
             const uint32_t g = first_cur + pg, stage = g % kStages;
             feed_pages(g);
             __syncwarp();
+            if (pg == 0) stamp(1, 6);
             mbar_wait(sm.full + stage, (g / kStages) & 1, a.error);
-            const unsigned char *p = sm.slab + (size_t) stage * page;
-            const unsigned char *pend = p + min(page, d_cur.bytes - pg * page);
-            while (p < pend) {
-                const uint4 h = *reinterpret_cast<const uint4 *>(p);
-                const unsigned char *rec = p;
-                p += (h.x >> 8) * 16;
-                if ((h.x & 0xff) != FR_LOADX) continue;
+            if (pg == 0) stamp(1, 7);
+            const unsigned char *p0 = sm.slab + (size_t) stage * page;
+            const unsigned char *pend = p0 + min(page, d_cur.bytes - pg * page);
+            // the page's directory (its first record) lists the staged records; more than six: walk the page
+            const uint4 dir = *reinterpret_cast<const uint4 *>(p0);
+            const uint32_t n_listed = dir.x >> 24;
+            const unsigned char *p = p0 + 16;
+            for (uint32_t li = 0;; ++li) {
+                const unsigned char *rec;
+                if (n_listed <= 6) {
+                    if (li >= n_listed) break;
+                    const uint32_t w = li < 2 ? dir.y : li < 4 ? dir.z : dir.w;
+                    rec = p0 + 16u * ((li & 1u) ? w >> 16 : w & 0xffffu);
+                } else {
+                    rec = nullptr;
+                    while (p < pend) {
+                        const uint32_t h0 = *reinterpret_cast<const uint32_t *>(p);
+                        const unsigned char *at = p;
+                        p += (h0 >> 8 & 0xffffu) * 16;
+                        if ((h0 & 0xff) == FR_LOADX) {
+                            rec = at;
+                            break;
+                        }
+                    }
+                    if (!rec) break;
+                }
+                const uint4 h = *reinterpret_cast<const uint4 *>(rec);
                 const int n_contig = (int) (h.y & 1023u), n_gather = (int) (h.y >> 10 & 1023u), n_extra = (int) (h.y >> 20 & 1023u);
                 const int cbuf = (int) (h.w & 15u), gkind = (int) (h.w >> 4 & 15u), n_wait = (int) (h.w >> 8);
                 const int *waits = reinterpret_cast<const int *>(rec + 16);
                 const int *glist = waits + ((n_wait + 3) & ~3);
-                // producers
-                for (int e = lane; e < n_wait; e += 32) {
-                    const int *flag = a.done + waits[e];
-                    unsigned spins = 0;
-                    unsigned long long t0 = 0;
-                    while (ld_acquire_gpu(flag) != epoch) {
-                        __nanosleep(100);  // thousands of loaders poll: keep their acquire loads (each invalidates L1) off the L2 queues
-                        if ((++spins & 4095u) == 0) {
-                            const unsigned long long now = global_ns();
-                            if (t0 == 0) t0 = now;
-                            if (now - t0 > kWatchdogNs || *(volatile int *) a.error != 0) {
-                                atomicExch(a.error, 2);
-                                break;
+                // producers.  The last two flags seen set are remembered: consecutive chunks of one producer cost one poll.
+                bool polled = false;
+                if (!(n_wait == 1 && (waits[0] == seen0 || waits[0] == seen1)) && n_wait > 0) {
+                    polled = true;
+                    for (int e = lane; e < n_wait; e += 32) {
+                        const int *flag = a.done + waits[e];
+                        unsigned spins = 0;
+                        unsigned long long t0 = 0;
+                        while (ld_acquire_gpu(flag) != epoch) {
+                            __nanosleep(100);  // thousands of loaders poll: keep their acquire loads (each invalidates L1) off the L2 queues
+                            if ((++spins & 4095u) == 0) {
+                                const unsigned long long now = global_ns();
+                                if (t0 == 0) t0 = now;
+                                if (now - t0 > kWatchdogNs || *(volatile int *) a.error != 0) {
+                                    atomicExch(a.error, 2);
+                                    break;
+                                }
                             }
                         }
                     }
+                    __syncwarp();
+                    seen1 = seen0;
+                    seen0 = waits[0];
                 }
-                __syncwarp();
-                fence_proxy_async();  // the producers' generic-proxy stores are read through the async proxy (TMA) below
+                // the producers' generic-proxy stores are read through the async proxy (TMA) below
+                if (polled) fence_proxy_async();
                 // ring space: a record's rows never wrap around the ring end; back-pressure on rows and barrier pairs
+                if (!traced_first) stamp(2, 5);
                 const int nr = n_contig + n_gather + n_extra;
                 int skipped = 0;
                 if (head + nr > ring_rows) skipped = ring_rows - head, head = 0;
@@ -371,6 +418,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
                     j_rel += 1;
                 }
                 __syncwarp();
+                if (!traced_first) stamp(2, 6);
                 const uint32_t slot = j_issue % kRowBars;
                 uint64_t *bar = sm.rfull + slot;
                 if (lane == 0) {
@@ -384,25 +432,36 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
                     tx += (uint32_t) n_contig * row_bytes;
                 }
                 F *gdst = sm.ring + (size_t) (head + n_contig) * kp;
-                if (gkind == 1) {
-                    for (int i = lane; i < n_gather; i += 32) tma_load_1d(gdst + (size_t) i * kp, a.tmp + (size_t) glist[i] * kp, row_bytes, bar);
-                    tx += (uint32_t) n_gather * row_bytes;
-                } else if (gkind == 2) {
-                    if (src_tma) {
-                        for (int i = lane; i < n_gather; i += 32)
-                            tma_load_1d(gdst + (size_t) i * kp, a.src + (size_t) glist[i] * k, src_row_bytes, bar);
-                        tx += (uint32_t) n_gather * src_row_bytes;
-                    } else {
-                        const int total = n_gather * k;
-#pragma unroll 1
-                        for (int e = lane; e < total; e += 32) {
-                            const int i = e / k, c = e - i * k;
-                            gdst[(size_t) i * kp + c] = __ldg(a.src + (size_t) glist[i] * k + c);
+                if (gkind == 1 || (gkind == 2 && src_tma)) {
+                    // gathered rows: 16 bytes per lane and instruction (cp.async), rows of the work vector or of the user's b
+                    const F *gsrc = gkind == 1 ? a.tmp : a.src;
+                    const uint32_t stride = gkind == 1 ? row_bytes : src_row_bytes;  // bytes between source rows == bytes per row
+                    const int cpr = (int) (stride / 16u);  // 16-byte chunks per row
+                    const unsigned char *gbase = reinterpret_cast<const unsigned char *>(gsrc) + 16 * lane;
+                    unsigned char *dbase = reinterpret_cast<unsigned char *>(gdst) + 16 * lane;
+                    for (int i0 = 0; i0 < n_gather; i0 += 32) {
+                        const int mine = i0 + lane < n_gather ? glist[i0 + lane] : 0;  // one index per lane, handed around below
+                        const int nrow = min(32, n_gather - i0);
+#pragma unroll 4
+                        for (int j = 0; j < nrow; ++j) {
+                            const size_t from = (size_t) __shfl_sync(kFullMask, mine, j) * stride;
+                            const size_t to = (size_t) (i0 + j) * row_bytes;
+                            for (int c = lane; c < cpr; c += 32) cp_async_16(dbase + to + 16 * (c - lane), gbase + from + 16 * (c - lane));
                         }
+                    }
+                    cp_async_arrive(bar);
+                } else if (gkind == 2) {
+                    const int total = n_gather * k;
+#pragma unroll 1
+                    for (int e = lane; e < total; e += 32) {
+                        const int i = e / k, c = e - i * k;
+                        gdst[(size_t) i * kp + c] = __ldg(a.src + (size_t) glist[i] * k + c);
                     }
                 }
                 __syncwarp();  // manual copies are complete before the arrival
                 if (lane == 0) mbar_expect_tx(bar, tx);
+                if (!traced_first) stamp(0, 6), stamp(2, 7);
+                traced_first = true;
                 j_issue += 1;
                 rows_in_flight += nr + skipped;
                 head += nr;
@@ -410,6 +469,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.empty + stage);
         }
+        stamp(0, 7);
         // next task becomes current
         know_next();
         t_cur = t_next;
@@ -439,8 +499,11 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
 
     // waits for staged record sj of the current task; returns its first ring row
     unsigned long long *t_first_ptr = nullptr, *t_wait_ptr = nullptr;
+    uint32_t staged_j = 0xffffffffu;  // last staged record this warp waited for, and its first ring row
+    int staged_base = 0;
     auto staged = [&](uint32_t sj) -> int {
         const uint32_t j = j0 + sj;
+        if (j == staged_j) return staged_base;
         if (a.trace && warp == 0) {
             const unsigned long long c0 = global_ns();
             mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
@@ -450,7 +513,9 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         } else {
             mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
         }
-        return sm.rows_base[j % kRowBars];
+        staged_j = j;
+        staged_base = sm.rows_base[j % kRowBars];
+        return staged_base;
     };
     auto store_dst = [&](int perm_row, const V &v) {
         F *d = a.dst + (size_t) perm_row * k + col;
@@ -500,7 +565,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
             }
             h = *reinterpret_cast<const uint4 *>(p);
             pay = p + 16;
-            p += (h.x >> 8) * 16;
+            p += (h.x >> 8 & 0xffffu) * 16;
             return true;
         };
         auto release = [&](uint32_t sj) {

@@ -67,7 +67,8 @@ struct FrontArgs {
     const Float *src;     // forward: user's b;  backward: null
     Float *dst;           // backward: user's x;  forward: null
     unsigned long long *trace;  // optional (debug): 8 words per task {start ns, CTA, end ns, first staged rows ready ns,
-                                // ns warp 0 spent waiting for staged rows, -, -, -}
+                                // ns warp 0 spent waiting for staged rows, loader: task start ns, first staged record issued ns,
+                                // task done ns}
 };
 
 }  // namespace chb

@@ -19,7 +19,7 @@ struct TaskDesc {
     uint32_t level;
 };
 
-enum { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE };
+enum { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE, FR_DIR };
 enum { FE_RING_SUB = 1, FE_RING_SET = 2, FE_Y = 4, FE_W = 8, FE_DST = 16 };
 constexpr int kMaxWarps = 8;
 
@@ -47,7 +47,8 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
             while (p < plen) {
                 uint32_t h[4];
                 std::memcpy(h, base + pg + p, 16);
-                const uint32_t type = h[0] & 0xff, len = (h[0] >> 8) * 16;
+                const uint32_t type = h[0] & 0xff, len = (h[0] >> 8 & 0xffff) * 16;
+                if ((p == 0) != (type == FR_DIR)) return -17;  // a directory record starts every page, and only there
                 if (len < 16 || p + len > plen) return -3;  // record straddles a page
                 const uint8_t *pay = base + pg + p + 16;
                 const int32_t *ipay = (const int32_t *) pay;
@@ -57,6 +58,27 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                 };
                 switch (type) {
                 case FR_NOP: case FR_BAR: break;
+                case FR_DIR: {
+                    // the directory must list exactly the page's staged records
+                    const uint32_t cnt = h[0] >> 24;
+                    uint32_t found = 0, q = 16;
+                    while (q < plen) {
+                        uint32_t g0;
+                        std::memcpy(&g0, base + pg + q, 4);
+                        if ((g0 & 0xff) == FR_LOADX) {
+                            if (found < 6 && cnt <= 6) {
+                                uint16_t units;
+                                std::memcpy(&units, base + pg + 4 + 2 * found, 2);
+                                if ((uint32_t) units * 16 != q) return -18;
+                            }
+                            found += 1;
+                        }
+                        if ((g0 >> 8 & 0xffff) == 0) return -18;
+                        q += (g0 >> 8 & 0xffff) * 16;
+                    }
+                    if (cnt != (found > 6 ? 7u : found)) return -18;
+                    break;
+                }
                 case FR_LOADX: {
                     const int n_contig = (int) (h[1] & 1023), n_gather = (int) (h[1] >> 10 & 1023), n_extra = (int) (h[1] >> 20 & 1023);
                     const int row0 = (int) h[2];

@@ -62,9 +62,9 @@ def main():
         od = np.ctypeslib.as_array(ctypes.cast(order, ctypes.POINTER(ctypes.c_int32)), shape=(nt,)).copy()
         sl = np.ctypeslib.as_array(ctypes.cast(slab, ctypes.POINTER(ctypes.c_uint32)), shape=(int(sinfo[1]) // 4,))
         off = (td[:, 0].astype(np.int64) | (td[:, 1].astype(np.int64) << 32)) // 4
-        # a local task's second record is FR_LROWS (after its FR_LOADX)
-        first_len = (sl[off] >> 8).astype(np.int64) * 4
-        local = (sl[off + first_len] & 0xff) == FR_LROWS
+        # a local task's third record is FR_LROWS (after the page directory and its FR_LOADX)
+        first_len = (sl[off + 4] >> 8 & 0xffff).astype(np.int64) * 4
+        local = (sl[off + 4 + first_len] & 0xff) == FR_LROWS
         ticket = np.empty(nt, np.int64)
         ticket[od] = np.arange(nt)
         t0 = tr[:, 0].min()
@@ -78,6 +78,17 @@ def main():
                 print("   %s: n %d, duration mean %.1f us p50 %.1f p90 %.1f max %.1f; wait mean %.1f us; start->first rows mean %.1f us; bytes mean %.0f" % (
                     nm, int(m.sum()), dur[m].mean() / 1e3, np.median(dur[m]) / 1e3, np.percentile(dur[m], 90) / 1e3, dur[m].max() / 1e3,
                     wait[m].mean() / 1e3, np.maximum(first[m] - start[m], 0).mean() / 1e3, td[m, 2].mean()))
+        ls, lf, ld = tr[:, 5] - t0, tr[:, 6] - t0, tr[:, 7] - t0
+        tsel = (int(os.environ.get("CHB_FRONT_DEBUG", "0")) >> 8) & 3
+        for nm, m in (("local", local), ("dense", ~local)):
+            if m.any() and tsel:
+                mm = m & (tr[:, 5] > 0) & (tr[:, 6] > 0) & (tr[:, 7] > 0)
+                print("   %s loader events (sel %d): w5 -> w6 %.2f us, w6 -> w7 %.2f us; compute start - w5 %.2f us; compute end - w7 %.2f us" % (
+                    nm, tsel, (lf - ls)[mm].mean() / 1e3, (ld - lf)[mm].mean() / 1e3, (start - ls)[mm].mean() / 1e3, (end - ld)[mm].mean() / 1e3))
+            elif m.any():
+                print("   %s loader: busy per task mean %.1f us (start -> first staged issue %.1f us); loader start -> compute start %.1f us; loader done -> compute end %.1f us" % (
+                    nm, (ld - ls)[m].mean() / 1e3, np.where(lf[m] > 0, lf[m] - ls[m], 0).mean() / 1e3, (start - ls)[m].mean() / 1e3,
+                    (end - ld)[m].mean() / 1e3))
         # gaps between consecutive tasks of one CTA
         o = np.lexsort((start, cta))
         same = cta[o][1:] == cta[o][:-1]
