@@ -522,57 +522,78 @@ struct FrontBuilder {
                 load[best] += group_w[(size_t) gi];
             }
         }
-        // levels among the upper INTERNAL rows (dependencies on subtree rows are covered by the phase order); the
-        // contribution rows (forward) depend on internal rows only and form one last phase
-        std::vector<int> level((size_t) n_rows_total, -1);
-        int n_lv = 0;
+        // What is emitted: "virtual rows" {target row, entries, pivot, accumulate from zero}.  A subtree row or a
+        // contribution row is one virtual row.  An UPPER row is split in two: (A) its entries from outside the upper set
+        // -- subtree rows forward, external rows backward, all final when the upper phase starts -- applied with pivot 1
+        // by any warp (one parallel phase), and (B) its entries from other upper rows plus the pivot, which form the
+        // short sequential chain at the top of the task.
+        struct VRow {
+            int row;
+            std::vector<Entry> ent;
+            double pivot;
+            bool from_zero;
+        };
+        std::vector<VRow> vrows;
+        std::vector<int> v_sub((size_t) n_int, -1), v_a((size_t) n_int, -1), v_b((size_t) n_int, -1), v_contrib;
         auto is_upper = [&](int r) { return r < n_int && group[(size_t) r] < 0; };
-        if (!upper) {
-            for (int r = 0; r < n_int; ++r) {
-                if (!is_upper(r)) continue;
-                int lv = 0;
-                for (const Entry &e : rows[(size_t) r])
-                    if (is_upper(e.idx)) lv = std::max(lv, level[(size_t) e.idx] + 1);
-                level[(size_t) r] = lv;
-                n_lv = std::max(n_lv, lv + 1);
-            }
-        } else {
-            for (int r = n_int - 1; r >= 0; --r) {
-                if (!is_upper(r)) continue;
-                int lv = 0;
-                for (const Entry &e : rows[(size_t) r])
-                    if (e.idx < n_int && is_upper(e.idx)) lv = std::max(lv, level[(size_t) e.idx] + 1);
-                level[(size_t) r] = lv;
-                n_lv = std::max(n_lv, lv + 1);
+        for (int r = 0; r < n_rows_total; ++r) {
+            if (r >= n_int) {
+                v_contrib.push_back((int) vrows.size());
+                vrows.push_back(VRow{r, rows[(size_t) r], -1.0, true});  // stored as +sum: consumers subtract
+            } else if (!is_upper(r)) {
+                v_sub[(size_t) r] = (int) vrows.size();
+                vrows.push_back(VRow{r, rows[(size_t) r], 1.0 / diag[(size_t) r], false});
+            } else {
+                VRow a{r, {}, 1.0, false}, b{r, {}, 1.0 / diag[(size_t) r], false};
+                for (const Entry &e : rows[(size_t) r]) (is_upper(e.idx) ? b.ent : a.ent).push_back(e);
+                if (!a.ent.empty()) {
+                    v_a[(size_t) r] = (int) vrows.size();
+                    vrows.push_back(std::move(a));
+                }
+                v_b[(size_t) r] = (int) vrows.size();
+                vrows.push_back(std::move(b));
             }
         }
-        // level by level (a barrier each, ~8 cost units) or all upper rows one after the other on one warp?
+        auto vcost = [&](int v) { return (int64_t) vrows[(size_t) v].ent.size() / 4 + 2; };
+        // levels among the (B) parts of the upper rows
+        std::vector<int> level((size_t) n_int, -1);
+        int n_lv = 0;
+        for (int q = 0; q < n_int; ++q) {
+            const int r = upper ? n_int - 1 - q : q;  // dependencies first
+            if (!is_upper(r)) continue;
+            int lv = 0;
+            for (const Entry &e : vrows[(size_t) v_b[(size_t) r]].ent) lv = std::max(lv, level[(size_t) e.idx] + 1);
+            level[(size_t) r] = lv;
+            n_lv = std::max(n_lv, lv + 1);
+        }
+        // (B) level by level (a barrier each, ~8 cost units) or one after the other on one warp?
         bool upper_serial = false;
         {
             std::vector<int64_t> lv_max((size_t) n_lv, 0);
             int64_t serial = 0;
             for (int r = 0; r < n_int; ++r)
                 if (level[(size_t) r] >= 0) {
-                    serial += cost_of(r);
-                    lv_max[(size_t) level[(size_t) r]] = std::max(lv_max[(size_t) level[(size_t) r]], cost_of(r));
+                    serial += vcost(v_b[(size_t) r]);
+                    lv_max[(size_t) level[(size_t) r]] = std::max(lv_max[(size_t) level[(size_t) r]], vcost(v_b[(size_t) r]));
                 }
             int64_t leveled = 0;
             for (int64_t v : lv_max) leveled += v + 8;
             upper_serial = serial <= leveled;
         }
-        img.n_local_levels += (upper_serial ? (n_lv > 0 ? 1 : 0) : n_lv) + 1 + (n_out > 0 ? 1 : 0);
-        img.n_local_rows += n_rows_total;
+        img.n_local_levels += (n_lv > 0 ? 1 : 0) + (upper_serial ? (n_lv > 0 ? 1 : 0) : n_lv) + 1 + (n_out > 0 ? 1 : 0);
+        img.n_local_rows += (int64_t) vrows.size();
         const size_t head_bytes = 2 * (size_t) es;  // {u32 meta, pivot}: pivot at byte es, indices from byte 2 es
-        auto row_bytes = [&](int r) {
-            const size_t n4 = (rows[(size_t) r].size() + 3) / 4;
+        auto row_bytes = [&](int v) {
+            const size_t n4 = (vrows[(size_t) v].ent.size() + 3) / 4;
             return round16(head_bytes + 4 * n4) + 4 * n4 * (size_t) es;
         };
-        std::vector<std::vector<int>> of_warp((size_t) NW);
+        std::vector<std::vector<int>> of_warp((size_t) NW);  // virtual rows of the phase being emitted, per warp, in order
         // one phase: every warp substitutes its list in order; records as large as the pages allow; then a barrier
         auto emit_phase = [&]() {
             size_t at_w[kFrontMaxWarps] = {0};
             size_t left = 0;
             for (const auto &v : of_warp) left += v.size();
+            if (left == 0) return;
             while (left > 0) {
                 size_t room = w.room_in_page();
                 if (room < 16 + 48 + 256) room = (size_t) img.page_bytes - w.page_overhead();
@@ -604,13 +625,12 @@ struct FrontBuilder {
                 for (int wi = 0; wi < NW; ++wi) {
                     w.put_int(off, (size_t) wi, (int32_t) (at - off));
                     for (size_t q = 0; q < take[wi]; ++q) {
-                        const int r = of_warp[(size_t) wi][at_w[wi] + q];
-                        const bool contribution = r >= n_int;  // accumulated from zero, no pivot; stored as +sum (consumers subtract)
-                        const std::vector<Entry> &ent = rows[(size_t) r];
+                        const VRow &vr = vrows[(size_t) of_warp[(size_t) wi][at_w[wi] + q]];
+                        const std::vector<Entry> &ent = vr.ent;
                         const size_t n4 = (ent.size() + 3) / 4;
                         if (n4 > 255) throw std::logic_error("front schedule: local row too long");
-                        w.put_int(at, 0, (int32_t) ((uint32_t) r | (uint32_t) n4 << 8 | (contribution ? 1u << 16 : 0u)));
-                        w.put_value(at + (size_t) es, 0, contribution ? -1.0 : 1.0 / diag[(size_t) r]);
+                        w.put_int(at, 0, (int32_t) ((uint32_t) vr.row | (uint32_t) n4 << 8 | (vr.from_zero ? 1u << 16 : 0u)));
+                        w.put_value(at + (size_t) es, 0, vr.pivot);
                         uint8_t idx[1024];
                         // padding entries (value 0) name the row's first source: a finished, finite row
                         for (size_t i = 0; i < 4 * n4; ++i) idx[i] = (uint8_t) (i < ent.size() ? ent[i].idx : ent[0].idx);
@@ -627,67 +647,59 @@ struct FrontBuilder {
             }
             emit_bar();
         };
+        // deals virtual rows to the warps, longest first, each to the least loaded warp
+        auto deal = [&](std::vector<int> vs) {
+            std::stable_sort(vs.begin(), vs.end(), [&](int x, int y) { return vrows[(size_t) x].ent.size() > vrows[(size_t) y].ent.size(); });
+            int64_t load[kFrontMaxWarps] = {0};
+            for (auto &v : of_warp) v.clear();
+            for (int v : vs) {
+                int best = 0;
+                for (int wi = 1; wi < NW; ++wi)
+                    if (load[wi] < load[best]) best = wi;
+                of_warp[(size_t) best].push_back(v);
+                load[best] += vcost(v);
+            }
+            emit_phase();
+        };
         auto subtree_phase = [&]() {
             for (auto &v : of_warp) v.clear();
             for (int q = 0; q < n_int; ++q) {
                 const int r = upper ? n_int - 1 - q : q;
-                if (group[(size_t) r] >= 0) of_warp[(size_t) warp_of_group[(size_t) group[(size_t) r]]].push_back(r);
+                if (group[(size_t) r] >= 0) of_warp[(size_t) warp_of_group[(size_t) group[(size_t) r]]].push_back(v_sub[(size_t) r]);
             }
             emit_phase();
         };
         auto upper_phases = [&]() {
             if (n_lv == 0) return;
+            std::vector<int> as;
+            for (int r = 0; r < n_int; ++r)
+                if (v_a[(size_t) r] >= 0) as.push_back(v_a[(size_t) r]);
+            deal(as);
             if (upper_serial) {
                 for (auto &v : of_warp) v.clear();
                 for (int q = 0; q < n_int; ++q) {
                     const int r = upper ? n_int - 1 - q : q;
-                    if (level[(size_t) r] >= 0) of_warp[0].push_back(r);
+                    if (level[(size_t) r] >= 0) of_warp[0].push_back(v_b[(size_t) r]);
                 }
                 emit_phase();
                 return;
             }
-            std::vector<std::vector<int>> by_level((size_t) n_lv);
-            for (int r = 0; r < n_int; ++r)
-                if (level[(size_t) r] >= 0) by_level[(size_t) level[(size_t) r]].push_back(r);
             for (int lv = 0; lv < n_lv; ++lv) {
-                std::vector<int> &rs = by_level[(size_t) lv];
-                std::stable_sort(rs.begin(), rs.end(), [&](int x, int y) { return rows[(size_t) x].size() > rows[(size_t) y].size(); });
-                int64_t load[kFrontMaxWarps] = {0};
-                for (auto &v : of_warp) v.clear();
-                for (int r : rs) {  // longest rows first, each to the least loaded warp
-                    int best = 0;
-                    for (int wi = 1; wi < NW; ++wi)
-                        if (load[wi] < load[best]) best = wi;
-                    of_warp[(size_t) best].push_back(r);
-                    load[best] += cost_of(r);
-                }
-                emit_phase();
+                std::vector<int> vs;
+                for (int r = 0; r < n_int; ++r)
+                    if (level[(size_t) r] == lv) vs.push_back(v_b[(size_t) r]);
+                deal(vs);
             }
-        };
-        auto contribution_phase = [&]() {
-            if (n_out == 0) return;
-            std::vector<int> rs;
-            for (int r = n_int; r < n_rows_total; ++r) rs.push_back(r);
-            std::stable_sort(rs.begin(), rs.end(), [&](int x, int y) { return rows[(size_t) x].size() > rows[(size_t) y].size(); });
-            int64_t load[kFrontMaxWarps] = {0};
-            for (auto &v : of_warp) v.clear();
-            for (int r : rs) {
-                int best = 0;
-                for (int wi = 1; wi < NW; ++wi)
-                    if (load[wi] < load[best]) best = wi;
-                of_warp[(size_t) best].push_back(r);
-                load[best] += cost_of(r);
-            }
-            emit_phase();
         };
         if (!upper) {
             subtree_phase();
             upper_phases();
-            contribution_phase();
+            deal(v_contrib);
         } else {
             upper_phases();
             subtree_phase();
         }
+        if (vrows.empty()) emit_bar();
         {
             const size_t off = w.record(FR_LSTORE, (uint32_t) n_int | (uint32_t) n_out << 16, (uint32_t) sj, (uint32_t) loc.c_lo,
                                         16 + (upper ? 4 * pad4((size_t) n_int) : 0));

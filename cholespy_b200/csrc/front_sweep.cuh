@@ -496,6 +496,22 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
 
     uint32_t gpage = 0;      // global index of the current task's first page
     uint32_t j0 = 0;         // sequence number of the task's first staged record
+    // tracing only: ns spent by warp 0 per activity {0 queue wait, 1 page wait, 2 staged wait, 3 MMA, 4 EPI, 5 ASM, 6 BAR,
+    // 7 REL, 8 LROWS, 9 LSTORE, 10 end barrier, 11 flag release, 12 other}
+    unsigned long long prof[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) prof[i] = 0;
+    const bool profiling = a.trace != nullptr && warp == 0;
+    unsigned long long pt = profiling ? global_ns() : 0;
+    auto lap = [&](int slot) {
+        if (profiling) {
+            const unsigned long long now = global_ns();
+#pragma unroll
+            for (int i = 0; i < 13; ++i)
+                if (i == slot) prof[i] += now - pt;
+            pt = now;
+        }
+    };
 
     // waits for staged record sj of the current task; returns its first ring row
     unsigned long long *t_first_ptr = nullptr, *t_wait_ptr = nullptr;
@@ -504,6 +520,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
     auto staged = [&](uint32_t sj) -> int {
         const uint32_t j = j0 + sj;
         if (j == staged_j) return staged_base;
+        lap(12);
         if (a.trace && warp == 0) {
             const unsigned long long c0 = global_ns();
             mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
@@ -515,6 +532,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         }
         staged_j = j;
         staged_base = sm.rows_base[j % kRowBars];
+        lap(2);
         return staged_base;
     };
     auto store_dst = [&](int perm_row, const V &v) {
@@ -529,7 +547,9 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
     };
 
     for (uint32_t q = 0;; ++q) {
+        lap(12);
         mbar_wait(sm.tfull + q % kTaskQueue, (q / kTaskQueue) & 1, a.error);
+        lap(0);
         const QueuedTask cur = sm.queue[q % kTaskQueue];
         if (cur.ticket >= a.n_tasks) break;
         const int task = cur.task;
@@ -557,7 +577,9 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                 if (pg == n_pages) return false;
                 const uint32_t g = gpage + pg;
                 stage = g % kStages;
+                lap(12);
                 mbar_wait(sm.full + stage, (g / kStages) & 1, a.error);
+                lap(1);
                 p = sm.slab + (size_t) stage * page;
                 pend = p + min(page, total - pg * page);
                 pg += 1;
@@ -618,7 +640,9 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                                     for (int c = 0; c < CPL; ++c) acc[i][c] = fma(av[i], x.v[c], acc[i][c]);
                             }
                         }
+                        lap(3);
                     } else if (type == FR_EPI) {
+                        lap(12);
                         const int t = warp - (int) (h.y & 255u);
                         const uint32_t mode = h.y >> 16;
                         if (t >= 0 && t < (int) (h.y >> 8 & 255u) && !(dbg & 32)) {
@@ -648,18 +672,24 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                                 }
                             }
                         }
+                        lap(4);
                         break;  // the epilogue ends the accumulation
                     } else if (type == FR_REL) {
+                        lap(12);
                         release(h.y);
+                        lap(7);
                     } else if (type == FR_LOADX) {
                         n_staged += 1;
                     } else if (type == FR_BAR) {
+                        lap(12);
                         if (!(dbg & 4)) named_barrier(1, NW * 32);
+                        lap(6);
                     }
                     if (!next_record(h, pay)) break;  // (malformed stream: an accumulation without epilogue)
                     type = h.x & 0xff;
                 }
             } else if (type == FR_ASM) {
+                lap(12);
                 // ring[row] -= W[w_row] for this warp's entries, 8-16 row loads in flight
                 const int *ip = reinterpret_cast<const int *>(pay);
                 const int lo = ip[warp], hi = ip[warp + 1];
@@ -688,13 +718,19 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                         }
                     }
                 }
+                lap(5);
             } else if (type == FR_BAR) {
+                lap(12);
                 if (!(dbg & 4)) named_barrier(1, NW * 32);
+                lap(6);
             } else if (type == FR_REL) {
+                lap(12);
                 release(h.y);
+                lap(7);
             } else if (type == FR_LOADX) {
                 n_staged += 1;
             } else if (type == FR_LROWS && !(dbg & 1)) {
+                lap(12);
                 // sparse rows of one dependency level of a local task: this warp substitutes its rows in place, over all
                 // RHS columns (CPL per lane)
                 const int *ip = reinterpret_cast<const int *>(pay);
@@ -749,7 +785,9 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                         qp = reinterpret_cast<const unsigned char *>(val + 4 * n4);
                     }
                 }
+                lap(8);
             } else if (type == FR_LSTORE && !(dbg & 2)) {
+                lap(12);
                 const int n_int = (int) (h.y & 0xffffu), n_ext = (int) (h.y >> 16);
                 const int *ip = reinterpret_cast<const int *>(pay);
                 const F *rows = sm.ring + (size_t) staged(h.z) * kp + lcol;
@@ -763,6 +801,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                     F *wrow = a.wbuf + (size_t) ip[0] * kp + col;
                     for (int e = warp; e < n_ext; e += NW) st_global<F, CPL>(wrow + (size_t) e * kp, ld_shared<F, CPL>(rows + (size_t) (n_int + e) * kp));
                 }
+                lap(9);
             }
             // FR_NOP: nothing
         }
@@ -770,7 +809,9 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         j0 += n_staged;
 
         // publish: every compute warp's stores of this task are done before the flag is released
+        lap(12);
         named_barrier(1, NW * 32);
+        lap(10);
         if (leader) {
             if (a.trace) {
                 a.trace[8 * (size_t) task + 2] = global_ns();
@@ -780,6 +821,11 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
             st_release_gpu(a.done + task, a.epoch);
             mbar_arrive(sm.tempty + q % kTaskQueue);
         }
+        lap(11);
+    }
+    if (profiling && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 13; ++i) a.trace[8 * (size_t) a.n_tasks + 16 * (size_t) blockIdx.x + i] = prof[i];
     }
 }
 

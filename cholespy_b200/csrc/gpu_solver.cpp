@@ -176,8 +176,10 @@ void GpuSolver::allocate_sweep(SweepDev &s) {
     cuda_check(cuMemsetD32Async(s.done, 0, (size_t) std::max(s.n_tasks, 1), nullptr));
     const char *trace = std::getenv("CHB_TRACE");
     if (trace && std::atoi(trace) != 0) {
-        s.trace = dev_alloc(sizeof(unsigned long long) * 8 * (size_t) s.n_tasks);
-        cuda_check(cuMemsetD8Async(s.trace, 0, sizeof(unsigned long long) * 8 * (size_t) s.n_tasks, nullptr));
+        // 8 words per task + 16 words per CTA (time spent by compute warp 0 per record type, front kernels)
+        const size_t words = 8 * (size_t) s.n_tasks + 16 * 4096;
+        s.trace = dev_alloc(sizeof(unsigned long long) * words);
+        cuda_check(cuMemsetD8Async(s.trace, 0, sizeof(unsigned long long) * words, nullptr));
     }
 }
 
@@ -185,7 +187,7 @@ size_t GpuSolver::copy_trace(bool upper, unsigned long long *out, size_t cap) {
     const SweepDev &s = m_sweep[upper ? 1 : 0];
     if (!s.trace) return 0;
     ContextGuard guard(m_dev);
-    const size_t words = std::min(cap, (size_t) 8 * (size_t) s.n_tasks);
+    const size_t words = std::min(cap, (size_t) 8 * (size_t) s.n_tasks + 16 * 4096);
     d2h(out, s.trace, sizeof(unsigned long long) * words);
     sync0();
     return words;

@@ -1,1 +1,1 @@
-for d in 63 319 575; do echo "== CHB_FRONT_DEBUG=$d"; CHB_FRONT_DEBUG=$d timeout 200 python scripts/trace_front.py ico8 f 128 gpurun_out/trace_front_ico8_dbg$d.npz 2>&1 | grep -E "^fwd|^bwd|local|dense"; done
+timeout 200 python scripts/trace_front.py ico8 f 128 gpurun_out/trace_front_ico8_prof.npz 2>&1 | grep -E "^fwd|^bwd|local|dense"

@@ -50,10 +50,16 @@ def main():
     res = {}
     for upper, key in ((0, "fwd"), (1, "bwd")):
         nt = info[key + "_tasks"]
-        buf = np.zeros(8 * nt, np.uint64)
+        buf = np.zeros(8 * nt + 16 * 4096, np.uint64)
         got = lib.chb_solver_get_trace(h, upper, buf.ctypes.data, buf.size)
         assert got == buf.size, (got, buf.size)
-        tr = buf.reshape(nt, 8).astype(np.int64)
+        tr = buf[:8 * nt].reshape(nt, 8).astype(np.int64)
+        prof = buf[8 * nt:].reshape(4096, 16)[:grid, :13].astype(np.float64)
+        names = ["queue wait", "page wait", "staged wait", "MMA", "EPI", "ASM", "BAR", "REL", "LROWS", "LSTORE", "end barrier",
+                 "flag release", "other"]
+        tot = prof.sum()
+        print("%s: compute warp 0 time by activity (all CTAs): " % key + ", ".join(
+            "%s %.1f%%" % (nm, 100 * prof[:, i].sum() / tot) for i, nm in enumerate(names)) + "; mean total per CTA %.2f ms" % (prof.sum(axis=1).mean() / 1e6))
         slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         sinfo = (ctypes.c_int64 * 19)()
         lib.chb_front_schedule_sweep(hs, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), sinfo, 19)
