@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-_LIB_PATH = os.path.join(_LIB_DIR, "libcholespy_b200.so")
+_LIB_PATH = os.path.join(_LIB_DIR, "libcholespy_b200%s.so" % (("_" + os.environ["CHB_LIB_VARIANT"]) if os.environ.get("CHB_LIB_VARIANT") else ""))
 
 OK, ERR_INVALID, ERR_RUNTIME = 0, 1, 2
 F32, F64 = 0, 1

@@ -222,7 +222,7 @@ struct Smem {
 };
 
 // ---- the loader warp -------------------------------------------------------------------------------
-template <typename F, int NW>
+template <typename F, int NW, bool TRACE>
 __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F> &sm, int lane) {
     const int k = a.k, kp = (k + 3) & ~3;
     const int ring_rows = a.ring_rows;
@@ -275,7 +275,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
         if (next_known) return;
         d_next = broadcast(s_next);
         next_known = true;
-        if (t_next < a.n_tasks && (a.debug & 64)) prefetch_l2(d_next);
+        if (t_next < a.n_tasks && (TRACE && (a.debug & 64))) prefetch_l2(d_next);
     };
     // hands pages to TMA in global order while the ring has room; blocks only for page `must` (the one needed now)
     auto feed_pages = [&](uint32_t must) {
@@ -313,7 +313,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
 
     t_cur = __shfl_sync(kFullMask, draw(), 0);
     d_cur = broadcast(load_desc(t_cur));
-    if (t_cur < a.n_tasks && (a.debug & 64)) prefetch_l2(d_cur);
+    if (t_cur < a.n_tasks && (TRACE && (a.debug & 64))) prefetch_l2(d_cur);
     t_next = __shfl_sync(kFullMask, draw(), 0);
     first_cur = 0;
     for (;;) {
@@ -330,7 +330,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
         // in flight from here on, consumed later: the next task's descriptor and the ticket after it
         s_next = load_desc(t_next);
         next_known = false;
-        t_nn = draw();
+        t_nn = (TRACE && (a.debug & 256)) ? draw() : 0;
         if (lane == 0) {
             if (q >= kTaskQueue) mbar_wait(sm.tempty + q % kTaskQueue, ((q / kTaskQueue) - 1) & 1, a.error);
             sm.queue[q % kTaskQueue] = QueuedTask{t_cur, (int) d_cur.level, d_cur.bytes, 0u};
@@ -338,9 +338,9 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
         }
         q += 1;
         bool traced_first = false;
-        const int tsel = (a.debug >> 8) & 3;  // which three loader events go to trace words 5..7
+        const int tsel = TRACE ? (a.debug >> 10) & 3 : 0;  // which three loader events go to trace words 5..7
         auto stamp = [&](int sel, int word) {
-            if (a.trace && lane == 0 && tsel == sel) a.trace[8 * (size_t) d_cur.level + word] = global_ns();
+            if (TRACE && a.trace && lane == 0 && tsel == sel) a.trace[8 * (size_t) d_cur.level + word] = global_ns();
         };
         stamp(0, 5);
         stamp(1, 5);
@@ -432,8 +432,15 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
                     tx += (uint32_t) n_contig * row_bytes;
                 }
                 F *gdst = sm.ring + (size_t) (head + n_contig) * kp;
-                if (gkind == 1 || (gkind == 2 && src_tma)) {
-                    // gathered rows: 16 bytes per lane and instruction (cp.async), rows of the work vector or of the user's b
+                if ((gkind == 1 || (gkind == 2 && src_tma)) && !(TRACE && (a.debug & 128))) {
+                    // gathered rows: one bulk copy per row, rows dealt to the lanes
+                    const F *gsrc = gkind == 1 ? a.tmp : a.src;
+                    const uint32_t stride = gkind == 1 ? row_bytes : src_row_bytes;
+                    for (int i = lane; i < n_gather; i += 32)
+                        tma_load_1d(gdst + (size_t) i * kp, reinterpret_cast<const unsigned char *>(gsrc) + (size_t) glist[i] * stride, stride, bar);
+                    tx += (uint32_t) n_gather * stride;
+                } else if (gkind == 1 || (gkind == 2 && src_tma)) {
+                    // (experiment, CHB_FRONT_DEBUG bit 128) 16 bytes per lane and instruction (cp.async)
                     const F *gsrc = gkind == 1 ? a.tmp : a.src;
                     const uint32_t stride = gkind == 1 ? row_bytes : src_row_bytes;  // bytes between source rows == bytes per row
                     const int cpr = (int) (stride / 16u);  // 16-byte chunks per row
@@ -475,12 +482,12 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
         t_cur = t_next;
         d_cur = d_next;
         first_cur = first_next;
-        t_next = __shfl_sync(kFullMask, t_nn, 0);
+        t_next = __shfl_sync(kFullMask, (TRACE && (a.debug & 256)) ? t_nn : draw(), 0);
     }
 }
 
 // ---- the compute warps -----------------------------------------------------------------------------
-template <typename F, int CPL, int NW>
+template <typename F, int CPL, int NW, bool TRACE>
 __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F> &sm, int warp, int lane) {
     constexpr int TR = Tile<F>::rows;
     constexpr int AV = 16 / (int) sizeof(F);     // factor values per 16-byte shared load
@@ -492,22 +499,22 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
     const int lcol = active ? col : 0;           // a column this lane may always read
     const bool leader = warp == 0 && lane == 0;
     const bool dst_vec = a.dst_vec != 0;
-    const int dbg = a.debug;
+    const int dbg = TRACE ? a.debug : 0;  // experiment switches exist in the tracing kernels only
 
     uint32_t gpage = 0;      // global index of the current task's first page
     uint32_t j0 = 0;         // sequence number of the task's first staged record
     // tracing only: ns spent by warp 0 per activity {0 queue wait, 1 page wait, 2 staged wait, 3 MMA, 4 EPI, 5 ASM, 6 BAR,
     // 7 REL, 8 LROWS, 9 LSTORE, 10 end barrier, 11 flag release, 12 other}
-    unsigned long long prof[13];
+    unsigned long long prof[TRACE ? 13 : 1];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) prof[i] = 0;
-    const bool profiling = a.trace != nullptr && warp == 0;
+    for (int i = 0; i < (TRACE ? 13 : 1); ++i) prof[i] = 0;
+    const bool profiling = TRACE && a.trace != nullptr && warp == 0;
     unsigned long long pt = profiling ? global_ns() : 0;
     auto lap = [&](int slot) {
-        if (profiling) {
+        if (TRACE && profiling) {
             const unsigned long long now = global_ns();
 #pragma unroll
-            for (int i = 0; i < 13; ++i)
+            for (int i = 0; i < (TRACE ? 13 : 1); ++i)
                 if (i == slot) prof[i] += now - pt;
             pt = now;
         }
@@ -521,7 +528,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         const uint32_t j = j0 + sj;
         if (j == staged_j) return staged_base;
         lap(12);
-        if (a.trace && warp == 0) {
+        if (TRACE && a.trace && warp == 0) {
             const unsigned long long c0 = global_ns();
             mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1, a.error);
             const unsigned long long c1 = global_ns();
@@ -557,7 +564,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         const uint32_t n_pages = (total + page - 1) / page;
         unsigned long long t_first_data = 0, t_wait = 0;  // tracing only (warp 0)
         t_first_ptr = &t_first_data, t_wait_ptr = &t_wait;
-        if (a.trace && leader) {
+        if (TRACE && a.trace && leader) {
             a.trace[8 * (size_t) task] = global_ns();
             a.trace[8 * (size_t) task + 1] = blockIdx.x;
         }
@@ -813,7 +820,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         named_barrier(1, NW * 32);
         lap(10);
         if (leader) {
-            if (a.trace) {
+            if (TRACE && a.trace) {
                 a.trace[8 * (size_t) task + 2] = global_ns();
                 a.trace[8 * (size_t) task + 3] = t_first_data;
                 a.trace[8 * (size_t) task + 4] = t_wait;
@@ -823,13 +830,13 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         }
         lap(11);
     }
-    if (profiling && lane == 0) {
+    if (TRACE && profiling && lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 13; ++i) a.trace[8 * (size_t) a.n_tasks + 16 * (size_t) blockIdx.x + i] = prof[i];
+        for (int i = 0; i < (TRACE ? 13 : 1); ++i) a.trace[8 * (size_t) a.n_tasks + 16 * (size_t) blockIdx.x + i] = prof[i];
     }
 }
 
-template <typename F, int CPL, int NW>
+template <typename F, int CPL, int NW, bool TRACE>
 __device__ __forceinline__ void front_worker(const FrontArgs<F> &a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -857,17 +864,20 @@ __device__ __forceinline__ void front_worker(const FrontArgs<F> &a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (warp == NW) loader_warp<F, NW>(a, sm, lane);
-    else compute_warp<F, CPL, NW>(a, sm, warp, lane);
+    if (warp == NW) loader_warp<F, NW, TRACE>(a, sm, lane);
+    else compute_warp<F, CPL, NW, TRACE>(a, sm, warp, lane);
 }
 
 }  // namespace front
 
 // Two CTA shapes: 7 compute warps + loader (256 threads, 2 CTAs per SM) and 4 + loader (160 threads, 3 per SM);
 // both leave 128 registers per thread (4 warps per scheduler).  The image is built for one of them (n_warps).
-#define CHB_FRONT(NAME, T, CPL, NW, MINB)                                                                \
-    extern "C" __global__ void __launch_bounds__(32 * (NW + 1), MINB) NAME(const chb::FrontArgs<T> a) {   \
-        front::front_worker<T, CPL, NW>(a);                                                              \
+#define CHB_FRONT(NAME, T, CPL, NW, MINB)                                                                       \
+    extern "C" __global__ void __launch_bounds__(32 * (NW + 1), MINB) NAME(const chb::FrontArgs<T> a) {          \
+        front::front_worker<T, CPL, NW, false>(a);                                                              \
+    }                                                                                                           \
+    extern "C" __global__ void __launch_bounds__(32 * (NW + 1), MINB) NAME##_trace(const chb::FrontArgs<T> a) {  \
+        front::front_worker<T, CPL, NW, true>(a);                                                               \
     }
 
 CHB_FRONT(chb_front_f32_c1_w7, float, 1, 7, 2)

@@ -487,7 +487,8 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
 void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst) {
     const SweepDev &s = m_sweep[upper ? 1 : 0];
     char name[64];
-    snprintf(name, sizeof name, "chb_front_%s_c%d_w%d", m_elem == 4 ? "f32" : "f64", front_cpl(k), s.n_warps);
+    // the tracing kernels (CHB_TRACE=1) also carry the experiment switches of CHB_FRONT_DEBUG
+    snprintf(name, sizeof name, "chb_front_%s_c%d_w%d%s", m_elem == 4 ? "f32" : "f64", front_cpl(k), s.n_warps, s.trace ? "_trace" : "");
     CUfunction fn = kernel(m_dev, name);
     if (!fn) throw std::runtime_error(driver_error_text());
     const int max_stage = std::max(m_sweep[0].max_stage_rows, m_sweep[1].max_stage_rows);
