@@ -758,29 +758,18 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                         } else {
                             sv = ld_shared<F, CPL>(dst);
                         }
-                        // the next group's indices and values are fetched while this group's source rows are in flight
-                        uint32_t i4n = 0;
-                        Vec<F, AV> vn[4 / AV];
-                        if (n4 > 0) {
-                            i4n = *reinterpret_cast<const uint32_t *>(idx);
-#pragma unroll
-                            for (int j = 0; j < 4 / AV; ++j) vn[j] = ld_shared<F, AV>(val + j * AV);
-                        }
                         for (int g4 = 0; g4 < n4; ++g4) {
-                            const uint32_t i4 = i4n;
+                            const uint32_t i4 = *reinterpret_cast<const uint32_t *>(idx + 4 * g4);
                             F vv[4];
 #pragma unroll
-                            for (int j = 0; j < 4 / AV; ++j)
+                            for (int j = 0; j < 4; j += AV) {
+                                const Vec<F, AV> v0 = ld_shared<F, AV>(val + 4 * g4 + j);
 #pragma unroll
-                                for (int jj = 0; jj < AV; ++jj) vv[j * AV + jj] = vn[j].v[jj];
+                                for (int jj = 0; jj < AV; ++jj) vv[j + jj] = v0.v[jj];
+                            }
                             V xs[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) xs[j] = ld_shared<F, CPL>(lrow + (size_t) (i4 >> (8 * j) & 0xff) * kp);
-                            if (g4 + 1 < n4) {
-                                i4n = *reinterpret_cast<const uint32_t *>(idx + 4 * (g4 + 1));
-#pragma unroll
-                                for (int j = 0; j < 4 / AV; ++j) vn[j] = ld_shared<F, AV>(val + 4 * (g4 + 1) + j * AV);
-                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
 #pragma unroll
