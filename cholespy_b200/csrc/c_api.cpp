@@ -382,7 +382,9 @@ CHB_API int chb_front_schedule_sweep(const chb_front_schedule *s, int upper, con
     const int64_t v[] = {(int64_t) img.tasks.size(), (int64_t) img.slab.size(), img.page_bytes, img.tile_rows, img.n_w_rows,
                          img.max_stage_rows, img.n_levels, img.n_values, img.n_stored_values, img.n_local_tasks,
                          img.n_dense_tasks, img.n_mma, img.n_asm_entries, s->structure.ns, (int64_t) s->structure.locals.size(),
-                         s->structure.n_blocks, img.n_warps, img.n_local_levels, img.n_local_rows};
+                         s->structure.n_blocks, img.n_warps, img.n_local_levels, img.n_local_rows,
+                         img.local_phase_groups[0], img.local_phase_groups[1], img.local_phase_groups[2], img.local_phase_groups[3],
+                         img.local_phase_rows[0], img.local_phase_rows[1], img.local_phase_rows[2], img.local_phase_rows[3]};
     int m = (int) (sizeof(v) / sizeof(v[0]));
     if (cap < m) m = cap;
     std::memcpy(info, v, sizeof(int64_t) * (size_t) m);

@@ -589,11 +589,22 @@ struct FrontBuilder {
         };
         std::vector<std::vector<int>> of_warp((size_t) NW);  // virtual rows of the phase being emitted, per warp, in order
         // one phase: every warp substitutes its list in order; records as large as the pages allow; then a barrier
+        int phase_kind = 0;
         auto emit_phase = [&]() {
             size_t at_w[kFrontMaxWarps] = {0};
             size_t left = 0;
             for (const auto &v : of_warp) left += v.size();
             if (left == 0) return;
+            {
+                int64_t worst_g = 0, worst_r = 0;
+                for (const auto &v : of_warp) {
+                    int64_t g = 0;
+                    for (int x : v) g += (int64_t) (vrows[(size_t) x].ent.size() + 3) / 4;
+                    if (g + (int64_t) v.size() > worst_g + worst_r) worst_g = g, worst_r = (int64_t) v.size();
+                }
+                img.local_phase_groups[phase_kind] += worst_g;
+                img.local_phase_rows[phase_kind] += worst_r;
+            }
             while (left > 0) {
                 size_t room = w.room_in_page();
                 if (room < 16 + 48 + 256) room = (size_t) img.page_bytes - w.page_overhead();
@@ -662,6 +673,7 @@ struct FrontBuilder {
             emit_phase();
         };
         auto subtree_phase = [&]() {
+            phase_kind = 0;
             for (auto &v : of_warp) v.clear();
             for (int q = 0; q < n_int; ++q) {
                 const int r = upper ? n_int - 1 - q : q;
@@ -674,7 +686,55 @@ struct FrontBuilder {
             std::vector<int> as;
             for (int r = 0; r < n_int; ++r)
                 if (v_a[(size_t) r] >= 0) as.push_back(v_a[(size_t) r]);
+            phase_kind = 1;
             deal(as);
+            phase_kind = 2;
+            // (B) as one dense step: the upper rows' coupling among themselves is a small triangular system T x = v
+            // (T = the entries between upper rows and the pivots, in processing order); x = inv(T) v is a dense
+            // product every warp does for its rows at once (FR_LTOP), instead of a chain of short dependent rows.
+            std::vector<int> tops;
+            for (int q = 0; q < n_int; ++q) {
+                const int r = upper ? n_int - 1 - q : q;
+                if (level[(size_t) r] >= 0) tops.push_back(r);
+            }
+            const int T = (int) tops.size();
+            if (T >= 2 && T <= 4 * NW) {
+                std::vector<int> pos((size_t) n_int, -1);
+                for (int pq = 0; pq < T; ++pq) pos[(size_t) tops[(size_t) pq]] = pq;
+                std::vector<double> M((size_t) T * T, 0.0), inv((size_t) T * T, 0.0);
+                for (int pq = 0; pq < T; ++pq) {
+                    const int r = tops[(size_t) pq];
+                    M[(size_t) pq * T + pq] = diag[(size_t) r];
+                    for (const Entry &e : vrows[(size_t) v_b[(size_t) r]].ent) {
+                        const int qq = pos[(size_t) e.idx];
+                        if (qq < 0 || qq >= pq) throw std::logic_error("front schedule: upper rows of a local task are not triangular");
+                        M[(size_t) pq * T + qq] += e.v;
+                    }
+                }
+                for (int c = 0; c < T; ++c)
+                    for (int i = c; i < T; ++i) {
+                        double acc = i == c ? 1.0 : 0.0;
+                        for (int q2 = c; q2 < i; ++q2) acc -= M[(size_t) i * T + q2] * inv[(size_t) q2 * T + c];
+                        inv[(size_t) i * T + c] = acc / M[(size_t) i * T + i];
+                    }
+                // payload: T row indices (u8, padded to 16 bytes); then per warp T x 4 coefficients: [q][i] = inv[w + i n_warps][q]
+                const size_t idx_bytes = round16((size_t) T);
+                const size_t off = w.record(FR_LTOP, (uint32_t) T, (uint32_t) sj, 0, idx_bytes + (size_t) NW * T * 4 * (size_t) es);
+                uint8_t idx[256];
+                for (int pq = 0; pq < T; ++pq) idx[pq] = (uint8_t) tops[(size_t) pq];
+                w.put_bytes(off, idx, (size_t) T);
+                for (int wi = 0; wi < NW; ++wi)
+                    for (int qq = 0; qq < T; ++qq)
+                        for (int i = 0; i < 4; ++i) {
+                            const int pq = wi + i * NW;
+                            w.put_value(off + idx_bytes, ((size_t) wi * T + qq) * 4 + i, pq < T ? inv[(size_t) pq * T + qq] : 0.0);
+                        }
+                img.n_stored_values += (int64_t) NW * T * 4;
+                img.local_phase_groups[2] += (T + 3) / 4;
+                img.local_phase_rows[2] += 1;
+                emit_bar();
+                return;
+            }
             if (upper_serial) {
                 for (auto &v : of_warp) v.clear();
                 for (int q = 0; q < n_int; ++q) {
@@ -694,6 +754,7 @@ struct FrontBuilder {
         if (!upper) {
             subtree_phase();
             upper_phases();
+            phase_kind = 3;
             deal(v_contrib);
         } else {
             upper_phases();

@@ -79,6 +79,11 @@ enum FrontRecord : uint32_t {
     // First record of every page (16 bytes): bits 24-31 of the header word = number of FR_LOADX records in the page
     // (7: more than six, walk the page), then six u16 offsets of those records, in 16-byte units from the page start.
     FR_DIR = 9,
+    // a = T (<= 4 n_warps), b = sj.  The upper rows of a local task, coupled among themselves by a small triangular
+    // system: x = inv(T) v as a dense product.  payload: T local row indices (u8, padded to 16 bytes); per warp w,
+    // T x 4 coefficients [q][i] = inv[w + i n_warps][q].  Every warp forms its (<= 4) rows from the CURRENT values of
+    // all T rows, a barrier, then stores them.
+    FR_LTOP = 10,
 };
 enum FrontEpiMode : uint32_t {
     FE_RING_SUB = 1,  // ring[row] -= acc
@@ -117,6 +122,8 @@ struct FrontImage {
     int64_t n_stored_values = 0;     // values in the slab
     int64_t n_local_tasks = 0, n_dense_tasks = 0, n_mma = 0, n_asm_entries = 0;
     int64_t n_local_levels = 0, n_local_rows = 0;  // dependency levels / sparse rows over all local tasks
+    int64_t local_phase_groups[4] = {0, 0, 0, 0};   // critical-path entry groups (of 4) per phase kind: subtrees, upper A, upper B, contributions
+    int64_t local_phase_rows[4] = {0, 0, 0, 0};     // ... and rows on that critical path
 };
 
 // Supernode partition + local tasks shared by both sweeps.

@@ -46,7 +46,7 @@ constexpr int kRowBars = 16;     // staged records in flight
 constexpr int kTaskQueue = 4;    // task descriptors the loader may run ahead
 constexpr unsigned kFullMask = 0xffffffffu;
 
-enum : uint32_t { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE, FR_DIR };
+enum : uint32_t { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE, FR_DIR, FR_LTOP };
 enum : uint32_t { FE_RING_SUB = 1, FE_RING_SET = 2, FE_Y = 4, FE_W = 8, FE_DST = 16 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -782,6 +782,41 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
                     }
                 }
                 lap(8);
+            } else if (type == FR_LTOP) {
+                // the upper rows of a local task: x = inv(T) v as a dense product; this warp forms rows warp, warp + NW, ...
+                // (at most 4) from the current values of all T rows, then -- after a barrier -- stores them
+                const int T = (int) h.y;
+                const unsigned char *idx = pay;
+                const F *coef = reinterpret_cast<const F *>(pay + ((T + 15) & ~15)) + (size_t) warp * T * 4;
+                F *lrow = sm.ring + (size_t) staged(h.z) * kp + lcol;
+                V o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) o[i].v[c] = F(0);
+                if (warp < T) {
+#pragma unroll 2
+                    for (int qq = 0; qq < T; ++qq) {
+                        const V x = ld_shared<F, CPL>(lrow + (size_t) idx[qq] * kp);
+                        F cf[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j += AV) {
+                            const Vec<F, AV> v0 = ld_shared<F, AV>(coef + 4 * qq + j);
+#pragma unroll
+                            for (int jj = 0; jj < AV; ++jj) cf[j + jj] = v0.v[jj];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) o[i].v[c] = fma(cf[i], x.v[c], o[i].v[c]);
+                    }
+                }
+                named_barrier(1, NW * 32);
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (warp + i * NW < T) st_shared<F, CPL>(lrow + (size_t) idx[warp + i * NW] * kp, o[i]);
+                }
             } else if (type == FR_LSTORE && !(dbg & 2)) {
                 lap(12);
                 const int n_int = (int) (h.y & 0xffffu), n_ext = (int) (h.y >> 16);

@@ -19,7 +19,7 @@ struct TaskDesc {
     uint32_t level;
 };
 
-enum { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE, FR_DIR };
+enum { FR_NOP = 0, FR_LOADX, FR_MMA, FR_EPI, FR_ASM, FR_BAR, FR_REL, FR_LROWS, FR_LSTORE, FR_DIR, FR_LTOP };
 enum { FE_RING_SUB = 1, FE_RING_SET = 2, FE_Y = 4, FE_W = 8, FE_DST = 16 };
 constexpr int kMaxWarps = 8;
 
@@ -224,6 +224,25 @@ int run(const uint8_t *slab, const TaskDesc *tasks, const int32_t *order, int n_
                             q = (const uint8_t *) (val + 4 * n4);
                         }
                     }
+                    break;
+                }
+                case FR_LTOP: {
+                    const int T = (int) h[1];
+                    std::vector<F> *st = stage(h[2]);
+                    if (!st || T < 1 || T > 4 * kWarps) return -19;
+                    const int rows_avail = (int) (st->size() / (size_t) k);
+                    const uint8_t *idx = pay;
+                    const F *coef = (const F *) (pay + ((T + 15) & ~15));
+                    std::vector<F> out((size_t) T * k, F(0));
+                    for (int pq = 0; pq < T; ++pq) {
+                        const int wi = pq % kWarps, i = pq / kWarps;
+                        if ((int) idx[pq] >= rows_avail) return -19;
+                        for (int qq = 0; qq < T; ++qq) {
+                            const F cf = coef[((size_t) wi * T + qq) * 4 + i];
+                            for (int c = 0; c < k; ++c) out[(size_t) pq * k + c] = fmadd(cf, (*st)[(size_t) idx[qq] * k + c], out[(size_t) pq * k + c]);
+                        }
+                    }
+                    for (int pq = 0; pq < T; ++pq) std::memcpy(&(*st)[(size_t) idx[pq] * k], &out[(size_t) pq * k], sizeof(F) * (size_t) k);
                     break;
                 }
                 case FR_LSTORE: {

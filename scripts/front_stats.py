@@ -32,9 +32,12 @@ def main():
     es = 4 if dt == "f" else 8
     for upper in (0, 1):
         slab, tasks, order = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-        info = (ctypes.c_int64 * 19)()
-        lib.chb_front_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 19)
-        info = dict(zip(FRONT_INFO_KEYS, list(info)))
+        info = (ctypes.c_int64 * 27)()
+        lib.chb_front_schedule_sweep(h, upper, ctypes.byref(slab), ctypes.byref(tasks), ctypes.byref(order), info, 27)
+        raw = list(info)
+        info = dict(zip(FRONT_INFO_KEYS, raw))
+        print("  local critical path per task: groups (subtrees, upper A, upper B, contributions) = %s, rows = %s" % (
+            [round(x / max(info["n_local_tasks"], 1), 1) for x in raw[19:23]], [round(x / max(info["n_local_tasks"], 1), 1) for x in raw[23:27]]))
         nt = info["n_tasks"]
         td = np.ctypeslib.as_array(ctypes.cast(tasks, ctypes.POINTER(ctypes.c_uint32)), shape=(nt, 4))
         nbytes, level = td[:, 2].astype(np.int64), td[:, 3]
