@@ -4,8 +4,8 @@
 // What it replaces: the plain CSR/CSC upload + per-row level list of the reference
 // (reference: src/cholesky_solver.cpp:245-288, 299-376) as the operand of solve_lower / solve_upper
 // (kernels/kernels.cu:64-202).  The reference's level arrays are still computed and exported bit-exactly
-// (GpuSolver::analyze); this schedule is internal.  Round 1's panel/block image (panel_schedule.h) is kept
-// for CHB_EXACT_ORDER=1 (reference summation order, bit-identical results).
+// (GpuSolver::analyze); this schedule is internal.  It is the ALTERNATIVE image (CHB_SWEEP=front): the panel/block
+// image (panel_schedule.h) is the default, being faster on every workload measured so far.
 //
 // Why a second layout (profiles/r01z_ncu_sweep_cfg4_summary.txt): the panel/block kernels spent 79 % of
 // their issue slots on record interpretation (16-row blocks of a few sources each, 1.6-1.75x zero fill)

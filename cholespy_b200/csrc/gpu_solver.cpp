@@ -296,12 +296,13 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     m_perm_host = L.perm;
 
     // Host: lay the factor out as the two sweep images (one thread each) while the device runs the
-    // level analysis of both triangles.  Default: the front image (front_schedule.h); round 1's panel image keeps
-    // the reference's summation order (CHB_EXACT_ORDER=1) and stays selectable with CHB_SWEEP=panel.
+    // level analysis of both triangles.  Default: the panel image (panel_schedule.h), the faster of the two on every
+    // measured workload; CHB_SWEEP=front selects the supernodal front image (front_schedule.h).
+    // CHB_EXACT_ORDER=1 (reference summation order) exists for the panel image only.
     const ScheduleOptions opt = schedule_options_from_env();
     m_exact = opt.exact_order;
     const char *mode = std::getenv("CHB_SWEEP");
-    m_front = !m_exact && !(mode && std::strcmp(mode, "panel") == 0);
+    m_front = !m_exact && mode && std::strcmp(mode, "front") == 0;
     const FrontOptions fopt = front_options_from_env(m_elem);
     PanelStructure structure;
     FrontStructure fstructure;

@@ -121,7 +121,7 @@ private:
     int m_sweeps = 0;
     int m_last_grid = 0;
     bool m_exact = false;       // exact-order schedule: packed triangles + IEEE division (the *_exact kernels)
-    bool m_front = true;        // front image + chb_front_* kernels (default); false: round 1's panel image (exact order, CHB_SWEEP=panel)
+    bool m_front = false;       // front image + chb_front_* kernels (CHB_SWEEP=front); default: the panel image + chb_sweep_* kernels
 
     TriangleAnalysis m_lower, m_upper;
     std::vector<int> m_perm_host;

@@ -3,8 +3,8 @@
 //
 // What they replace (reference: kernels/kernels.cu):
 //   chb_analysis            <- analysis_lower / analysis_upper   (:8-33, :35-60)
-//   chb_front_*  (front_sweep.cuh) <- solve_lower_* / solve_upper_*  (:64-131, :133-202)   [default]
-//   chb_sweep_*  (sweep.cuh)       <- the same, reference summation order (CHB_EXACT_ORDER=1)
+//   chb_sweep_*  (sweep.cuh)       <- solve_lower_* / solve_upper_*  (:64-131, :133-202)   [default; _exact: reference order]
+//   chb_front_*  (front_sweep.cuh) <- the same over the supernodal front image (CHB_SWEEP=front)
 //
 // chb_analysis: persistent co-resident grid, one warp per row, rows handed out in order by an atomic
 // ticket; the level word doubles as the ready flag (pre-set to -1), so a waiting row can never read a

@@ -326,3 +326,24 @@ def test_random_patterns_on_the_gpu(seed, oracle_mod, native_lib):
             b = rng.random((n, k)).astype(dtype)
             x = _gpu_solve(s, b)
             assert max_rel_err(x, oracle_mod.solve(cp, ri, v, perm, b)) < TOL[np.dtype(dtype)], (seed, n, k)
+
+
+# The alternative sweep image (csrc/front_schedule.h, kernels chb_front_*): selected per solver by CHB_SWEEP=front.
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("warps", ["7", "4"])
+@pytest.mark.parametrize("name", ["ico3", "ico5", "grid2d-40", "grid3d-10", "localspd-30"])
+def test_front_path_vs_oracle(name, warps, dtype, oracle_mod, native_lib, monkeypatch):
+    monkeypatch.setenv("CHB_SWEEP", "front")
+    monkeypatch.setenv("CHB_FRONT_WARPS", warps)
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    A = problems.to_scipy_csc(p)
+    s = _solver(p, dtype)
+    assert s.info()["front_image"] == 1 and s.info()["compute_warps"] == int(warps)
+    rng = np.random.default_rng(46)
+    for k in (1, 3, 4, 33, 64, 128):
+        b = rng.random((p["n"], k)).astype(dtype)
+        x = _gpu_solve(s, b)
+        x_or = oracle_mod.solve(cp, ri, v, perm, b)
+        assert max_rel_err(x, x_or) < TOL[np.dtype(dtype)], (name, k)
+        assert rel_residual(A, x, b) < (1e-5 if dtype == np.float32 else 1e-13), (name, k)
