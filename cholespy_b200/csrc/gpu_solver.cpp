@@ -288,6 +288,61 @@ void GpuSolver::analyze(TriangleAnalysis &t, const std::vector<int> &ptr, const 
     bucket_rows_by_level(t.level_of_row, t.n_levels, t.order_host);
 }
 
+// Both level arrays from the elimination tree (kernels.cu: chb_etree_round): forward level = height of the node,
+// backward level = depth.  The parent array (first below-diagonal row of every column of L) is read off the factor
+// on the host in O(n); the device doubles ancestor pointers, ceil(log2(height)) + 1 rounds of n threads.
+void GpuSolver::analyze_etree(const HostFactor &L) {
+    const int n = m_n;
+    std::vector<int> parent((size_t) n), ones((size_t) n);
+    for (int j = 0; j < n; ++j) {
+        parent[(size_t) j] = L.colptr[j + 1] - L.colptr[j] > 1 ? L.rowidx[(size_t) L.colptr[j] + 1] : -1;
+        ones[(size_t) j] = parent[(size_t) j] >= 0 ? 1 : 0;
+    }
+    const size_t bytes = sizeof(int) * (size_t) n;
+    void *buf[6];  // anc, dist, best: two copies each (a round reads one set and writes the other)
+    for (void *&b : buf) b = dev_alloc(bytes);
+    int *counters = (int *) m_counters;
+    h2d(buf[0], parent.data(), bytes);
+    h2d(buf[2], ones.data(), bytes);
+    cuda_check(cuMemsetD8Async(buf[4], 0, bytes, nullptr));
+    CUfunction fn = kernel(m_dev, "chb_etree_round");
+    if (!fn) throw std::runtime_error(driver_error_text());
+    int cur = 0, active = n > 0 ? 1 : 0;
+    for (int round = 0; round < 32 && active > 0; ++round) {
+        EtreeArgs args;
+        args.n = n;
+        args.step = 1 << round;
+        args.anc_in = (const int *) buf[0 + cur], args.anc_out = (int *) buf[0 + (cur ^ 1)];
+        args.dist_in = (const int *) buf[2 + cur], args.dist_out = (int *) buf[2 + (cur ^ 1)];
+        args.best_in = (const int *) buf[4 + cur], args.best_out = (int *) buf[4 + (cur ^ 1)];
+        args.active = counters + 2;
+        cuda_check(cuMemsetD8Async(args.best_out, 0, bytes, nullptr));
+        cuda_check(cuMemsetD32Async(counters + 2, 0, 1, nullptr));
+        void *params[] = {&args};
+        cuda_check(cuLaunchKernel(fn, (unsigned) ((n + 255) / 256), 1, 1, 256, 1, 1, 0, nullptr, params, nullptr));
+        d2h(&active, counters + 2, sizeof(int));
+        sync0();
+        cur ^= 1;
+    }
+    if (active > 0) throw std::runtime_error("elimination-tree analysis did not converge (the factor's tree is deeper than 2^32?)");
+    m_lower.level_of_row.resize((size_t) n);
+    m_upper.level_of_row.resize((size_t) n);
+    d2h(m_lower.level_of_row.data(), buf[4 + cur], bytes);  // height
+    d2h(m_upper.level_of_row.data(), buf[2 + cur], bytes);  // depth
+    sync0();
+    for (void *&b : buf) dev_free(b);
+    for (TriangleAnalysis *t : {&m_lower, &m_upper}) {
+        int max_level = 0;
+        for (int r = 0; r < n; ++r) {
+            if (t->level_of_row[(size_t) r] < 0 || t->level_of_row[(size_t) r] >= n)
+                throw std::runtime_error("level analysis produced an out-of-range level (GPU kernel failure)");
+            max_level = std::max(max_level, t->level_of_row[(size_t) r]);
+        }
+        t->n_levels = n > 0 ? max_level + 1 : 0;
+        bucket_rows_by_level(t->level_of_row, t->n_levels, t->order_host);
+    }
+}
+
 GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     : m_dev(require_device(device)), m_elem(elem_size), m_n(L.n), m_nnz(L.nnz()) {
     ContextGuard guard(m_dev);
@@ -322,12 +377,19 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
             }
         });
     try {
-        {
-            std::vector<int> rowptr, colidx;  // CSR of L (diagonal last per row): the forward operand
-            csc_to_csr_pattern(L.n, L.colptr, L.rowidx, rowptr, colidx);
-            analyze(m_lower, rowptr, colidx, true);
+        // CHB_ANALYSIS=rows: the row-by-row restatement of the reference's kernels (one warp per row, ready flags),
+        // kept as a cross-check; default: both level arrays from the elimination tree by pointer doubling
+        const char *amode = std::getenv("CHB_ANALYSIS");
+        if (amode && std::strcmp(amode, "rows") == 0) {
+            {
+                std::vector<int> rowptr, colidx;  // CSR of L (diagonal last per row): the forward operand
+                csc_to_csr_pattern(L.n, L.colptr, L.rowidx, rowptr, colidx);
+                analyze(m_lower, rowptr, colidx, true);
+            }
+            analyze(m_upper, L.colptr, L.rowidx, false);  // CSC of L == CSR of L' (diagonal first per row)
+        } else {
+            analyze_etree(L);
         }
-        analyze(m_upper, L.colptr, L.rowidx, false);  // CSC of L == CSR of L' (diagonal first per row)
     } catch (...) {
         for (auto &t : builders) t.join();
         throw;

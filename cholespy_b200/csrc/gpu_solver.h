@@ -107,6 +107,7 @@ public:
 private:
     void allocate_sweep(SweepDev &s);
     void analyze(TriangleAnalysis &t, const std::vector<int> &ptr, const std::vector<int> &idx, bool lower);
+    void analyze_etree(const HostFactor &L);
     void upload_sweep(SweepDev &d, const SweepImage &img);
     void sweep(bool upper, int k, const void *src, void *dst);
     void front_sweep(bool upper, int k, const void *src, void *dst);

@@ -15,6 +15,19 @@ struct AnalysisArgs {
     int *ticket;
 };
 
+// One doubling round of the elimination-tree analysis (kernels.cu: chb_etree_round).
+struct EtreeArgs {
+    int n;
+    int step;             // 2^round: distance covered by `anc_in`
+    const int *anc_in;    // 2^round-th ancestor of every node (-1: none)
+    int *anc_out;         // 2^(round+1)-th ancestor
+    const int *dist_in;   // number of tree edges from the node to anc_in (or to its root when anc_in == -1)
+    int *dist_out;
+    const int *best_in;   // longest downward path of < 2^round edges starting at the node
+    int *best_out;        // ... of < 2^(round+1) edges; must be zeroed before the round
+    int *active;          // incremented by every node that still has an ancestor pointer after the round
+};
+
 // One panel sweep (kernels.cu: chb_sweep_*).  See panel_schedule.h for the slab/record format.
 // Device task table, in TICKET order (dependencies first): entry t is what the worker drawing ticket t runs.
 struct SweepTask {

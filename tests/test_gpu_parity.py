@@ -347,3 +347,31 @@ def test_front_path_vs_oracle(name, warps, dtype, oracle_mod, native_lib, monkey
         x_or = oracle_mod.solve(cp, ri, v, perm, b)
         assert max_rel_err(x, x_or) < TOL[np.dtype(dtype)], (name, k)
         assert rel_residual(A, x, b) < (1e-5 if dtype == np.float32 else 1e-13), (name, k)
+
+
+def test_analysis_row_kernel_matches_etree_kernel(oracle_mod, native_lib, monkeypatch):
+    """The default analysis (elimination-tree heights / depths by pointer doubling, chb_etree_round) and the row-by-row
+    restatement of the reference's kernels (chb_analysis, CHB_ANALYSIS=rows) give the same arrays, on meshes and on
+    irregular random patterns (chains, stars, forests)."""
+    import scipy.sparse as sps
+    cases = [problems.build_problem(nm) for nm in ("ico4", "grid3d-8", "localspd-25")]
+    rng = np.random.default_rng(5)
+    for seed in range(4):
+        n = int(rng.integers(30, 400))
+        B = sps.random(n, n, density=float(rng.uniform(0.003, 0.03)), random_state=rng, format="csr")
+        A = (B @ B.T + sps.diags(rng.standard_normal(n - 1), -1, shape=(n, n)) @ sps.diags(rng.standard_normal(n - 1), 1, shape=(n, n))
+             + float(n) * sps.identity(n)).tocsc()
+        A = ((A + A.T) * 0.5).tocsc()
+        A.sort_indices()
+        cases.append(dict(n=n, ii=A.indptr.astype(np.int32), jj=A.indices.astype(np.int32), x=A.data.astype(np.float64), fmt="CSC"))
+    cases.append(dict(n=7, ii=np.arange(8, dtype=np.int32), jj=np.arange(7, dtype=np.int32), x=np.full(7, 2.0), fmt="CSC"))  # diagonal
+    for p in cases:
+        monkeypatch.delenv("CHB_ANALYSIS", raising=False)
+        a = _solver(p, np.float64)
+        monkeypatch.setenv("CHB_ANALYSIS", "rows")
+        b = _solver(p, np.float64)
+        for lower in (True, False):
+            la, oa = a.analysis(lower)
+            lb, ob = b.analysis(lower)
+            assert np.array_equal(la, lb) and np.array_equal(oa, ob)
+        assert a.info()["n_levels_lower"] == b.info()["n_levels_lower"] and a.info()["n_levels_upper"] == b.info()["n_levels_upper"]
