@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the cholespy solve path on B200: RHS-columns solved per second (L + L' sweeps).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl reference|reference-gpu]
 
 One step = one `.solve(b, x)` of the workload's system (forward + backward sweep over all RHS columns).
 Default workload: BASELINE.json's config the metric is quoted on -- cfg4, icosphere(9) I+10L,
-CholeskySolverF, 128 RHS (RHS columns sharded over the ranks when N > 1, strong scaling).
+CholeskySolverF, 128 RHS (RHS columns sharded over the ranks when N > 1: strong scaling, the default).
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
 
 Timing: CUDA events on the legacy default stream (the stream the kernels are launched on) around each
 solve, L2 flushed between steps, max over ranks.  `e2e` goes through the public API with pinned host
-buffers (H2D + solve + D2H inside the timed region).  `cpu_baseline` times the CPU oracle port on one
-core on a bounded column sample; `--impl reference` times the reference's own CHOLMOD solve_cpu
-(oracle/_ref, the reference sources compiled unmodified).
+buffers (H2D + solve + D2H inside the timed region).  `cpu_baseline` times the reference's own CHOLMOD
+solve_cpu on ONE core on a bounded column sample (oracle/_ref, the reference sources compiled unmodified; the C
+oracle port where that library is absent); `--impl reference` times the same solve_cpu fanned over all host cores;
+`--impl reference-gpu` times the reference's own GPU kernels (kernels/kernels.cu:64-202 through its solve_cuda,
+src/cholesky_solver.cpp:415-432) on the same B200 -- "the kernel to beat" of BASELINE.md section 3.
 """
 import argparse
 import ctypes
@@ -222,6 +224,79 @@ def run_reference(args, name, p, k, dtype):
 
 
 # ------------------------------------------------------------------------------------------------
+# reference GPU arm: the reference's own kernels on this B200
+# ------------------------------------------------------------------------------------------------
+def run_reference_gpu(args, name, p, k, dtype):
+    """Times CholeskySolver<Float>::solve_cuda of the REFERENCE (oracle/_ref: src/*.cpp compiled unmodified; its
+    shipped sm_30 PTX JIT-ed by the driver, or kernels/kernels.cu compiled for sm_100a if the driver refuses the PTX)
+    with CUDA events on the legacy stream, L2 flushed between steps.  The reference's analysis kernels race on a B200
+    (profiles/r01_reference_analysis_race.txt): a schedule that is not even a permutation is rejected and the
+    constructor retried; the caller should run this arm under a timeout (an invalid schedule can spin forever)."""
+    import torch
+    from oracle import oracle
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not oracle.reference_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/libcholespy_ref.so is not built"}), flush=True)
+        return
+    torch.cuda.set_device(0)
+    t = time.time()
+    ref, tries = None, 0
+    while ref is None and tries < 4:
+        tries += 1
+        try:
+            cand = oracle.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False)
+        except RuntimeError:
+            cand = oracle.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=False, use_sm100_cubin=True)
+        lo, up, _ = cand.schedule()
+        n = p["n"]
+        if np.array_equal(np.sort(lo), np.arange(n)) and np.array_equal(np.sort(up), np.arange(n)):
+            ref = cand
+        else:
+            log("reference analysis produced an invalid level order (race), retrying")
+            cand.close()
+    if ref is None:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "reference analysis never produced a valid level order"}), flush=True)
+        return
+    log("reference GPU constructor (CHOLMOD + its analysis kernels): %.1f s, %d attempt(s)" % (time.time() - t, tries))
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    b = torch.rand((p["n"], k), dtype=tdt, device="cuda", generator=torch.Generator(device="cuda").manual_seed(45))
+    x = torch.zeros_like(b)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(max(args.warmup, 1)):
+        ref.solve_cuda(k, b.data_ptr(), x.data_ptr())
+    torch.cuda.synchronize()
+    times = []
+    t_begin = time.time()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ref.solve_cuda(k, b.data_ptr(), x.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+        if time.time() - t_begin > args.ref_budget_s:
+            break
+    ms = float(np.mean(times))
+    A = to_csc(p)
+    xs = x[:, :min(k, 2)].double().cpu().numpy()
+    bs = b[:, :min(k, 2)].double().cpu().numpy()
+    resid = float((np.linalg.norm(A @ xs - bs, axis=0) / np.linalg.norm(bs, axis=0)).max())
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": k / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": len(times),
+            "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "none", "vs_baseline": None,
+            "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
+            "config": {"workload": workload_description(name, p, k, dtype), "kernels": "reference kernels/kernels.cu:64-202 (one 128-thread CTA per row)",
+                       "l2": "512 MB flush write between timed steps"},
+            "relative_residual": resid, "gpu_launches": 2 * len(times)}
+    print(json.dumps(line), flush=True)
+
+
+def to_csc(p):
+    return problems.to_scipy_csc(p)
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def build_solver(args, name, p, k, dtype, rank, world, device):
@@ -267,6 +342,14 @@ def run_b200(args, name, p, k_total, dtype):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # one disjoint block of host cores per rank: the pinned staging buffers are then first-touched (and the strided
+        # H2D / D2H copies driven) from different cores instead of all ranks piling onto the cores of NUMA node 0
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per] or cores))
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=device)
     from cholespy_b200 import _capi
     lib = _capi.load()
@@ -361,33 +444,62 @@ def run_b200(args, name, p, k_total, dtype):
         # algorithmic bytes = Bytes(k)/2, per-launch duration = step/2 (this rank's shard).
         abytes = algorithmic_bytes(n, z, k, s)
         achieved = abytes / (dev_ms * 1e-3) / 1e9
-        traffic = None  # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture, if any
+        # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture of THIS build: the entry names
+        # the kernels and the grid it was taken with and is ignored (traffic = null) if either differs from this run
+        traffic, traffic_source = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and world == 1:
-            traffic = json.load(open(tpath)).get("%s/k%d/%s" % (args.workload, k_total, "f32" if dtype == np.float32 else "f64"))
+            entry = json.load(open(tpath)).get("%s/k%d/%s" % (args.workload, k_total, "f32" if dtype == np.float32 else "f64"))
+            kernels = "chb_front" if info.get("front_image") else "chb_sweep"
+            if isinstance(entry, dict) and entry.get("grid") == info.get("grid") and str(entry.get("kernels", "")).startswith(kernels):
+                traffic, traffic_source = entry.get("bytes_per_launch"), entry.get("source")
+            elif entry is not None:
+                log("profiles/ncu_traffic.json entry does not match this build (grid/kernels): roofline.traffic = null")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_step": abytes,
+                    "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src, "algorithmic_bytes_per_step": abytes,
                     "launches_per_step": 2, "roofline_columns_per_s": k / (abytes / (peak * 1e9))}
         cpu_baseline = None
         if not args.no_cpu_baseline:
             from oracle import oracle
-            perm, cp, ri, v = get_factor(name, p)
-            ck = min(k_total, args.cpu_columns)
+            from helpers import max_rel_err, max_rel_err_elementwise
+            tol = 1e-5 if dtype == np.float32 else 1e-12
+            ck = max(1, min(k_total, args.cpu_columns))
             bc = np.random.default_rng(45).random((n, ck)).astype(dtype)
-            t0 = time.perf_counter()
-            xc = oracle.solve(cp, ri, v, perm, bc)
-            dt = time.perf_counter() - t0
-            cpu_baseline = {"value": ck / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                            "sample": "%d of %d RHS columns, one pass of the C oracle (oracle/cholespy_oracle.c), %.1f s" % (ck, k_total, dt)}
-            # the oracle doubles as a checker of the timed GPU result
             bt = torch.tensor(bc, device=device)
             xt = torch.zeros_like(bt)
             solver.solve(bt, xt)
             torch.cuda.synchronize()
-            err = float((np.abs(xt.cpu().numpy().astype(np.float64) - xc).max(axis=0) / np.abs(xc).max(axis=0)).max())
-            tol = 1e-5 if dtype == np.float32 else 1e-12
+            xg = xt.cpu().numpy()
+            if oracle.reference_available():
+                # the reference's own CPU path on ONE core: CholeskySolver<Float>::solve_cpu -> cholmod_solve
+                # (src/cholesky_solver.cpp:434-463), single-threaded by construction
+                t0 = time.perf_counter()
+                ref = oracle.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], dtype, cpu=True)
+                t_ctor = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                xc = ref.solve_cpu(bc)
+                dt = time.perf_counter() - t0
+                ref.close()
+                cpu_baseline = {"value": ck / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                                "sample": "%d of %d RHS columns, one call of the reference's solve_cpu (CHOLMOD, oracle/_ref), %.1f s "
+                                          "(its constructor, CHOLMOD analyze + factorize: %.0f s, not counted)" % (ck, k_total, dt, t_ctor)}
+                cpu_baseline["gpu_vs_cholmod_max_rel_err"] = max_rel_err(xg, xc)
+                cpu_baseline["gpu_vs_cholmod_max_rel_err_elementwise"] = max_rel_err_elementwise(xg, xc)
+                assert cpu_baseline["gpu_vs_cholmod_max_rel_err"] < tol, "GPU result differs from the reference's CHOLMOD solve: %g" % cpu_baseline["gpu_vs_cholmod_max_rel_err"]
+            # the C restatement of the reference's GPU kernels (oracle/cholespy_oracle.c) as the second checker, on
+            # fewer columns (it is a scalar loop); it is the timed baseline only where oracle/_ref is absent
+            perm, cp, ri, v = get_factor(name, p)
+            ok = ck if cpu_baseline is None else min(ck, 4)
+            t0 = time.perf_counter()
+            xo = oracle.solve(cp, ri, v, perm, np.ascontiguousarray(bc[:, :ok]))
+            dt = time.perf_counter() - t0
+            if cpu_baseline is None:
+                cpu_baseline = {"value": ok / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%d of %d RHS columns, one pass of the C oracle (oracle/cholespy_oracle.c), %.1f s" % (ok, k_total, dt)}
+            err = max_rel_err(xg[:, :ok], xo)
             assert err < tol, "GPU result differs from the oracle: %g" % err
             cpu_baseline["gpu_vs_oracle_max_rel_err"] = err
+            cpu_baseline["gpu_vs_oracle_max_rel_err_elementwise"] = max_rel_err_elementwise(xg[:, :ok], xo)
         line = {
             "metric": METRIC, "value": k_total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
@@ -414,21 +526,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--workload", default=os.environ.get("CHB_WORKLOAD", "cfg4"))
     ap.add_argument("--k", type=int, default=0, help="override the number of RHS columns")
     ap.add_argument("--dtype", default="", choices=["", "f", "d"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = every GPU solves the config's RHS columns (default); strong = they are split")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = the config's RHS columns are sharded over the GPUs (default: BASELINE.json's "
+                         "'128 RHS sharded over 1/2/4/8 GPUs'); weak = every GPU solves the config's columns of its own")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-columns", type=int, default=32, help="columns of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-columns", type=int, default=8, help="columns of the bounded CPU-baseline sample")
     ap.add_argument("--ref-procs", type=int, default=64, help="worker processes of the reference arm (capped at the core count)")
     ap.add_argument("--ref-budget-s", type=float, default=60.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
-    if args.impl == "reference" and rank != 0:
+    if args.impl != "b200" and rank != 0:
         return
     t = time.time()
     _, d_dtype, d_k = problems.resolve_workload(args.workload)
@@ -439,6 +552,8 @@ def main():
         log("problem %s built in %.1f s (n=%d, nnz(A)=%d)" % (args.workload, time.time() - t, p["n"], len(p["x"])))
     if args.impl == "reference":
         run_reference(args, args.workload, p, k, dtype)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args, args.workload, p, k, dtype)
     else:
         run_b200(args, args.workload, p, k, dtype)
 

@@ -215,6 +215,18 @@ class _CholeskySolver:
                 "front_image", "update_rows", "compute_warps")
         return dict(zip(keys[:m], list(out)[:m]))
 
+    def shard(self, devices):
+        """Shards the RHS columns of later solves over further GPUs (ordinals of the ADDITIONAL devices; [] undoes it).
+        New: the reference is single-device.  See include/cholespy_b200.h: chb_solver_shard."""
+        dev = np.ascontiguousarray(list(devices), np.int32)
+        _capi.check(_capi.load().chb_solver_shard(self._handle, len(dev), dev.ctypes.data if len(dev) else None))
+
+    def shard_info(self):
+        out = (ctypes.c_int64 * 4)()
+        _capi.load().chb_solver_shard_info(self._handle, out, 4)
+        return {"devices": int(out[0]), "replication": {0: "none", 1: "nccl", 2: "peer"}[int(out[1])], "bytes": int(out[2]),
+                "seconds": out[3] * 1e-6}
+
     def check_error(self):
         """Synchronises the device and raises RuntimeError if the sweep kernels' watchdog fired."""
         _capi.check(_capi.load().chb_solver_check_error(self._handle))

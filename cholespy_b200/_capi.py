@@ -36,6 +36,8 @@ _SIGNATURES = {
     "chb_solver_solve_host": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
     "chb_solver_solve_cpu": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
     "chb_solver_check_error": (ctypes.c_int, [c_vp]),
+    "chb_solver_shard": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
+    "chb_solver_shard_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "chb_solver_is_cpu": (ctypes.c_int, [c_vp]),
     "chb_solver_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "chb_solver_get_analysis": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),

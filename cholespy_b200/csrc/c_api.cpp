@@ -1,6 +1,7 @@
 // C ABI (include/cholespy_b200.h) over the C++ implementation.
 #include "cholespy_b200.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -8,10 +9,12 @@
 #include <vector>
 
 #include "cholesky_solver.h"
+#include "disk_cache.h"
 #include "factor_host.h"
 #include "front_schedule.h"
 #include "gpu_solver.h"
 #include "panel_schedule.h"
+#include "shard.h"
 
 #define CHB_API extern "C" __attribute__((visibility("default")))
 
@@ -20,6 +23,7 @@ struct chb_solver {
     CholeskySolver<float> *f32 = nullptr;    // full-constructor solvers (own the CHOLMOD state in CPU mode)
     CholeskySolver<double> *f64 = nullptr;
     chb::GpuSolver *bare = nullptr;          // from-factor / replica solvers
+    chb::ShardGroup *shards = nullptr;       // RHS columns sharded over further devices (chb_solver_shard / CHB_SHARD_GPUS)
     chb::GpuSolver *gpu() const { return bare ? bare : f32 ? f32->gpu() : f64 ? f64->gpu() : nullptr; }
     bool is_cpu() const { return !gpu(); }
 };
@@ -63,6 +67,22 @@ int guarded(Fn &&fn) {
     }
 }
 
+// CHB_SHARD_GPUS=N in the environment: every CUDA-mode solver shards its multi-RHS solves over N visible devices
+// (the solver's own device first), so that an unchanged cholespy program uses them.
+void shard_from_env(chb_solver *s) {
+    const char *v = std::getenv("CHB_SHARD_GPUS");
+    chb::GpuSolver *g = s->gpu();
+    if (!v || !g) return;
+    const int want = std::atoi(v);
+    if (want < 2) return;
+    int count = 0;
+    if (cuDeviceGetCount(&count) != CUDA_SUCCESS) return;
+    std::vector<int> others;
+    for (int d = 0; d < count && (int) others.size() + 1 < want; ++d)
+        if (d != g->device()) others.push_back(d);
+    if (!others.empty()) s->shards = new chb::ShardGroup(g, others);
+}
+
 void check_dtype(int dtype) {
     if (dtype != CHB_F32 && dtype != CHB_F64) throw std::invalid_argument("dtype must be CHB_F32 or CHB_F64");
 }
@@ -85,6 +105,7 @@ void fill_factor(chb::HostFactor &L, int n, int64_t nnz_l, const int32_t *l_colp
 }
 }  // namespace
 
+CHB_API void chb_solver_destroy(chb_solver *s);
 CHB_API const char *chb_last_error(void) { return t_error.c_str(); }
 CHB_API int chb_version(void) { return 100; }
 
@@ -118,8 +139,9 @@ CHB_API int chb_solver_create(chb_solver **out, int dtype, int n_rows, int nnz, 
                 s->f32 = new CholeskySolver<float>(n_rows, nnz, ii, jj, x, (MatrixType) matrix_type, cpu, device);
             else
                 s->f64 = new CholeskySolver<double>(n_rows, nnz, ii, jj, x, (MatrixType) matrix_type, cpu, device);
+            shard_from_env(s);
         } catch (...) {
-            delete s;
+            chb_solver_destroy(s);
             throw;
         }
         *out = s;
@@ -130,9 +152,13 @@ CHB_API int chb_solver_create_from_device_arrays(chb_solver **out, int dtype, in
                                                  const void *ii_dev, const void *jj_dev, const void *x_dev,
                                                  int matrix_type, int device) {
     // Stage the user's matrix to the host (CHOLMOD runs there), as src/main.cpp:55-61 does.
-    std::vector<int32_t> ii((size_t) len_ii), jj((size_t) nnz);
-    std::vector<double> x((size_t) nnz);
+    std::vector<int32_t> ii, jj;
+    std::vector<double> x;
     int rc = guarded([&] {
+        if (len_ii < 0 || nnz < 0) throw std::invalid_argument("Sparse matrix: negative array length.");
+        ii.resize((size_t) len_ii);
+        jj.resize((size_t) nnz);
+        x.resize((size_t) nnz);
         chb::DeviceState *d = chb::device_state(device);
         if (!d) throw std::runtime_error(chb::driver_error_text());
         scoped_set_context guard(d->ctx);
@@ -157,8 +183,9 @@ CHB_API int chb_solver_create_from_factor(chb_solver **out, int dtype, int n, in
         s->dtype = dtype;
         try {
             s->bare = new chb::GpuSolver(device, dtype == CHB_F32 ? 4 : 8, L);
+            shard_from_env(s);
         } catch (...) {
-            delete s;
+            chb_solver_destroy(s);
             throw;
         }
         *out = s;
@@ -192,6 +219,7 @@ CHB_API int chb_solver_create_replica(chb_solver **out, int dtype, const int64_t
 
 CHB_API void chb_solver_destroy(chb_solver *s) {
     if (!s) return;
+    delete s->shards;
     delete s->f32;
     delete s->f64;
     delete s->bare;
@@ -202,8 +230,30 @@ CHB_API int chb_solver_solve_cuda(chb_solver *s, int n_rhs, const void *b_dev, v
     return guarded([&] {
         chb::GpuSolver *g = s->gpu();
         if (!g) throw std::invalid_argument("Input device is CUDA but the solver was initialized for CPU.");
-        g->solve(n_rhs, b_dev, x_dev);
+        if (s->shards) s->shards->solve(n_rhs, b_dev, x_dev);
+        else g->solve_wide(n_rhs, b_dev, x_dev);
     });
+}
+
+CHB_API int chb_solver_shard(chb_solver *s, int n_devices, const int32_t *devices) {
+    return guarded([&] {
+        chb::GpuSolver *g = s->gpu();
+        if (!g) throw std::invalid_argument("CPU-mode solvers cannot be sharded over GPUs.");
+        delete s->shards;
+        s->shards = nullptr;
+        if (n_devices <= 0) return;
+        s->shards = new chb::ShardGroup(g, std::vector<int>(devices, devices + n_devices));
+    });
+}
+
+CHB_API int chb_solver_shard_info(const chb_solver *s, int64_t *out, int cap) {
+    const chb::ShardGroup *sh = s->shards;
+    const int64_t v[] = {sh ? sh->n_devices() : 1, sh ? (std::strcmp(sh->replication(), "nccl") == 0 ? 1 : std::strcmp(sh->replication(), "peer") == 0 ? 2 : 0) : 0,
+                         sh ? (int64_t) sh->replicated_bytes() : 0, sh ? (int64_t) (sh->replication_seconds() * 1e6) : 0};
+    int m = (int) (sizeof(v) / sizeof(v[0]));
+    if (cap < m) m = cap;
+    std::memcpy(out, v, sizeof(int64_t) * (size_t) m);
+    return m;
 }
 
 CHB_API int chb_solver_solve_host(chb_solver *s, int n_rhs, const void *b_host, void *x_host) {
@@ -282,7 +332,13 @@ CHB_API int chb_factorize(chb_factor **out, int n_rows, int nnz, const int32_t *
         chb::CscMatrix A = chb::intake_matrix(n_rows, nnz, ii, jj, x, (chb::MatrixFormat) matrix_type);
         chb_factor *f = new chb_factor();
         try {
-            chb::factorize_spd(A, &f->L, nullptr);
+            // CHB_CACHE_DIR set: the factor of a matrix seen before is read back instead of re-running CHOLMOD
+            const bool caching = !chb::cache_dir().empty();
+            const chb::CacheKey key = caching ? chb::matrix_key(A) : chb::CacheKey();
+            if (!caching || !chb::load_factor(key, &f->L)) {
+                chb::factorize_spd(A, &f->L, nullptr);
+                if (caching) chb::store_factor(key, f->L);
+            }
         } catch (...) {
             delete f;
             throw;

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <stdexcept>
 
+#include "disk_cache.h"
 #include "factor_host.h"
 #include "gpu_solver.h"
 
@@ -27,8 +28,15 @@ void CholeskySolver<Float>::build(int n_rows, int nnz, const int *ii, const int 
     if (m_cpu) {
         chb::factorize_spd(A, nullptr, &m_cholmod);
     } else {
+        // CHB_CACHE_DIR set: the factor of a matrix seen before is read back instead of re-running CHOLMOD
         chb::HostFactor L;
-        chb::factorize_spd(A, &L, nullptr);
+        const bool caching = !chb::cache_dir().empty();
+        chb::CacheKey key;
+        if (caching) key = chb::matrix_key(A);
+        if (!caching || !chb::load_factor(key, &L)) {
+            chb::factorize_spd(A, &L, nullptr);
+            if (caching) chb::store_factor(key, L);
+        }
         m_gpu = new chb::GpuSolver(device, (int) sizeof(Float), L);
     }
 }
@@ -55,7 +63,7 @@ CholeskySolver<Float>::~CholeskySolver() {
 template <typename Float>
 void CholeskySolver<Float>::solve_cuda(int n_rhs, CUdeviceptr b, CUdeviceptr x) {
     if (!m_gpu) throw std::invalid_argument("Input device is CUDA but the solver was initialized for CPU.");
-    m_gpu->solve(n_rhs, b, x);
+    m_gpu->solve_wide(n_rhs, b, x);
 }
 
 template <typename Float>

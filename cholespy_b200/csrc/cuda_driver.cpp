@@ -49,6 +49,9 @@ CUresult (*cuEventDestroy)(CUevent) = nullptr;
 CUresult (*cuEventRecord)(CUevent, CUstream) = nullptr;
 CUresult (*cuMemcpy2DAsync)(const CUDA_MEMCPY2D *, CUstream) = nullptr;
 CUresult (*cuPointerGetAttribute)(void *, int, CUdeviceptr) = nullptr;
+CUresult (*cuDeviceCanAccessPeer)(int *, CUdevice, CUdevice) = nullptr;
+CUresult (*cuCtxEnablePeerAccess)(CUcontext, unsigned int) = nullptr;
+CUresult (*cuMemcpyPeerAsync)(CUdeviceptr, CUcontext, CUdeviceptr, CUcontext, size_t, CUstream) = nullptr;
 
 CUdevice cu_device = 0;
 CUcontext cu_context = nullptr;
@@ -57,8 +60,9 @@ namespace {
 void *g_libcuda = nullptr;
 bool g_symbols_ok = false;
 std::mutex g_mutex;
-std::string g_error;
-CUresult g_first_error = CUDA_SUCCESS;
+std::string g_error;                                  // initialisation failures (set under g_mutex)
+thread_local CUresult g_first_error = CUDA_SUCCESS;   // per calling thread: concurrent C-ABI calls do not lose or
+thread_local std::string g_cuda_error;                // misattribute each other's CUDA errors
 std::map<int, chb::DeviceState *> g_devices;
 std::map<std::pair<int, std::string>, CUfunction> g_functions;
 
@@ -104,7 +108,9 @@ bool load_symbols() {
               resolve(cuStreamDestroy, "cuStreamDestroy_v2") && resolve(cuStreamWaitEvent, "cuStreamWaitEvent") &&
               resolve(cuEventCreate, "cuEventCreate") && resolve(cuEventDestroy, "cuEventDestroy_v2") &&
               resolve(cuEventRecord, "cuEventRecord") && resolve(cuMemcpy2DAsync, "cuMemcpy2DAsync_v2") &&
-              resolve(cuPointerGetAttribute, "cuPointerGetAttribute");
+              resolve(cuPointerGetAttribute, "cuPointerGetAttribute") &&
+              resolve(cuDeviceCanAccessPeer, "cuDeviceCanAccessPeer") && resolve(cuCtxEnablePeerAccess, "cuCtxEnablePeerAccess") &&
+              resolve(cuMemcpyPeerAsync, "cuMemcpyPeerAsync");
     if (!ok) return false;
     CUresult rc = cuInit(0);
     if (rc != CUDA_SUCCESS) {
@@ -125,16 +131,19 @@ void cuda_check_impl(CUresult errval, const char *file, const int line) {
             msg ? msg : "?", file, line);
     if (g_first_error == CUDA_SUCCESS) {
         g_first_error = errval;
-        g_error = std::string("CUDA error ") + std::to_string(errval) + " (" + (name ? name : "?") + ") at " + file + ":" +
+        g_cuda_error = std::string("CUDA error ") + std::to_string(errval) + " (" + (name ? name : "?") + ") at " + file + ":" +
                   std::to_string(line);
     }
 }
 CUresult cuda_first_error() { return g_first_error; }
-void cuda_clear_error() { g_first_error = CUDA_SUCCESS; }
+void cuda_clear_error() {
+    g_first_error = CUDA_SUCCESS;
+    g_cuda_error.clear();
+}
 
 namespace chb {
 
-const char *driver_error_text() { return g_error.c_str(); }
+const char *driver_error_text() { return g_cuda_error.empty() ? g_error.c_str() : g_cuda_error.c_str(); }
 
 DeviceState *device_state(int ordinal) {
     std::lock_guard<std::mutex> lock(g_mutex);

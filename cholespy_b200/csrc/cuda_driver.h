@@ -78,6 +78,9 @@ extern CUresult (*cuEventDestroy)(CUevent);
 extern CUresult (*cuEventRecord)(CUevent, CUstream);
 extern CUresult (*cuMemcpy2DAsync)(const CUDA_MEMCPY2D *, CUstream);
 extern CUresult (*cuPointerGetAttribute)(void *, int, CUdeviceptr);
+extern CUresult (*cuDeviceCanAccessPeer)(int *, CUdevice, CUdevice);
+extern CUresult (*cuCtxEnablePeerAccess)(CUcontext, unsigned int);
+extern CUresult (*cuMemcpyPeerAsync)(CUdeviceptr, CUcontext, CUdeviceptr, CUcontext, size_t, CUstream);
 
 #define cuda_check(err) cuda_check_impl(err, __FILE__, __LINE__)
 // Prints CUDA API failures to stderr and records the first one for chb_last_error(); never throws

@@ -21,7 +21,10 @@ CscMatrix intake_matrix(int n, int nnz, const int *ii, const int *jj, const doub
         std::memcpy(row_of.data(), ii, sizeof(int) * (size_t) nnz);
         std::memcpy(col_of.data(), jj, sizeof(int) * (size_t) nnz);
     } else {
-        // ii = pointer array (n+1), jj = minor indices
+        // ii = pointer array (n+1), jj = minor indices; a malformed pointer array must not index out of bounds
+        if (n < 0 || ii[0] != 0 || ii[n] != nnz) throw std::invalid_argument("Sparse matrix: invalid pointer array.");
+        for (int major = 0; major < n; ++major)
+            if (ii[major + 1] < ii[major]) throw std::invalid_argument("Sparse matrix: invalid pointer array.");
         for (int major = 0; major < n; ++major)
             for (int p = ii[major]; p < ii[major + 1]; ++p) {
                 if (fmt == FMT_CSC) { col_of[p] = major; row_of[p] = jj[p]; }

@@ -435,15 +435,16 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
                 if ((gkind == 1 || (gkind == 2 && src_tma)) && !(TRACE && (a.debug & 128))) {
                     // gathered rows: one bulk copy per row, rows dealt to the lanes
                     const F *gsrc = gkind == 1 ? a.tmp : a.src;
-                    const uint32_t stride = gkind == 1 ? row_bytes : src_row_bytes;
+                    const uint32_t bytes = gkind == 1 ? row_bytes : src_row_bytes;                                        // per row
+                    const size_t stride = gkind == 1 ? (size_t) row_bytes : (size_t) a.src_ld * sizeof(F);  // between source rows
                     for (int i = lane; i < n_gather; i += 32)
-                        tma_load_1d(gdst + (size_t) i * kp, reinterpret_cast<const unsigned char *>(gsrc) + (size_t) glist[i] * stride, stride, bar);
-                    tx += (uint32_t) n_gather * stride;
+                        tma_load_1d(gdst + (size_t) i * kp, reinterpret_cast<const unsigned char *>(gsrc) + (size_t) glist[i] * stride, bytes, bar);
+                    tx += (uint32_t) n_gather * bytes;
                 } else if (gkind == 1 || (gkind == 2 && src_tma)) {
                     // (experiment, CHB_FRONT_DEBUG bit 128) 16 bytes per lane and instruction (cp.async)
                     const F *gsrc = gkind == 1 ? a.tmp : a.src;
-                    const uint32_t stride = gkind == 1 ? row_bytes : src_row_bytes;  // bytes between source rows == bytes per row
-                    const int cpr = (int) (stride / 16u);  // 16-byte chunks per row
+                    const size_t stride = gkind == 1 ? (size_t) row_bytes : (size_t) a.src_ld * sizeof(F);  // bytes between source rows
+                    const int cpr = (int) ((gkind == 1 ? row_bytes : src_row_bytes) / 16u);  // 16-byte chunks per row
                     const unsigned char *gbase = reinterpret_cast<const unsigned char *>(gsrc) + 16 * lane;
                     unsigned char *dbase = reinterpret_cast<unsigned char *>(gdst) + 16 * lane;
                     for (int i0 = 0; i0 < n_gather; i0 += 32) {
@@ -462,7 +463,7 @@ __device__ __forceinline__ void loader_warp(const FrontArgs<F> &a, const Smem<F>
 #pragma unroll 1
                     for (int e = lane; e < total; e += 32) {
                         const int i = e / k, c = e - i * k;
-                        gdst[(size_t) i * kp + c] = __ldg(a.src + (size_t) glist[i] * k + c);
+                        gdst[(size_t) i * kp + c] = __ldg(a.src + (size_t) glist[i] * a.src_ld + c);
                     }
                 }
                 __syncwarp();  // manual copies are complete before the arrival
@@ -543,7 +544,7 @@ __device__ __forceinline__ void compute_warp(const FrontArgs<F> &a, const Smem<F
         return staged_base;
     };
     auto store_dst = [&](int perm_row, const V &v) {
-        F *d = a.dst + (size_t) perm_row * k + col;
+        F *d = a.dst + (size_t) perm_row * a.dst_ld + col;
         if (dst_vec) {
             *reinterpret_cast<V *>(d) = v;
         } else {

@@ -9,6 +9,7 @@
 #include <thread>
 #include <type_traits>
 
+#include "disk_cache.h"
 #include "kernel_args.h"
 
 namespace chb {
@@ -359,17 +360,38 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     const char *mode = std::getenv("CHB_SWEEP");
     m_front = !m_exact && mode && std::strcmp(mode, "front") == 0;
     const FrontOptions fopt = front_options_from_env(m_elem);
-    PanelStructure structure;
-    FrontStructure fstructure;
-    if (m_front) build_front_structure(L, m_elem, fopt, &fstructure);
-    else build_panel_structure(L, opt, &structure);
     SweepImage img[2];
     FrontImage fimg[2];
+    // CHB_CACHE_DIR set: images built before for this factor, element size and options are read back
+    const bool caching = !cache_dir().empty();
+    CacheKey key;
+    std::string tag;
+    bool cached = false;
+    if (caching) {
+        key = factor_key(L);
+        char buf[256];
+        if (m_front)
+            snprintf(buf, sizeof buf, "front e%d w%d lr%d le%d p%d f%d s%d o%d b%d", m_elem, fopt.warps, fopt.local_rows, fopt.local_ext,
+                     fopt.panel, fopt.fuse_steps, fopt.split_chunks, fopt.own_chunks, fopt.order_blocks);
+        else
+            snprintf(buf, sizeof buf, "panel e%d x%d lr%d le%d lc%d sc%d cc%d a%.4f b%.4f c%d i%d", m_elem, (int) opt.exact_order, opt.local_rows,
+                     opt.local_ext, opt.local_cost, opt.split_cost, opt.chunk_cost, opt.relax_alpha, opt.relax_beta, (int) opt.contributions,
+                     opt.inv_panels);
+        tag = buf;
+        cached = m_front ? load_front_images(key, tag, &fimg[0], &fimg[1]) : load_panel_images(key, tag, &img[0], &img[1]);
+    }
+    PanelStructure structure;
+    FrontStructure fstructure;
+    if (!cached) {
+        if (m_front) build_front_structure(L, m_elem, fopt, &fstructure);
+        else build_panel_structure(L, opt, &structure);
+    }
     std::exception_ptr errors[2];
     std::thread builders[2];
     for (int u = 0; u < 2; ++u)
         builders[u] = std::thread([&, u] {
             try {
+                if (cached) return;
                 if (m_front) build_front_image(L, fstructure, m_elem, u == 1, fopt, &fimg[u]);
                 else build_sweep_image(L, structure, m_elem, u == 1, opt, &img[u]);
             } catch (...) {
@@ -397,6 +419,10 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
     for (auto &t : builders) t.join();
     for (int u = 0; u < 2; ++u)
         if (errors[u]) std::rethrow_exception(errors[u]);
+    if (caching && !cached) {
+        if (m_front) store_front_images(key, tag, fimg[0], fimg[1]);
+        else store_panel_images(key, tag, img[0], img[1]);
+    }
     for (int u = 0; u < 2; ++u) {
         if (m_front) {
             upload_front(m_sweep[u], fimg[u]);
@@ -455,7 +481,7 @@ GpuSolver::~GpuSolver() {
     if (m_copy_in) {
         cuda_check(cuStreamDestroy(m_copy_in));
         cuda_check(cuStreamDestroy(m_copy_out));
-        for (int i = 0; i < 4; ++i) {
+        for (size_t i = 0; i < m_ev_in.size(); ++i) {
             cuda_check(cuEventDestroy(m_ev_in[i]));
             cuda_check(cuEventDestroy(m_ev_out[i]));
         }
@@ -493,7 +519,7 @@ std::vector<ImageBuffer> GpuSolver::image() const {
     return out;
 }
 
-void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
+void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
     char name[64];
     snprintf(name, sizeof name, "chb_sweep_%s_%s%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower", m_exact ? "_exact" : "");
     CUfunction fn = kernel(m_dev, name);
@@ -517,7 +543,9 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
         a.epoch = m_epoch;
         a.local_rows = local_rows;
         a.ring_rows = sweep_ring_rows(m_elem, k, local_rows);
-        a.src_tma = (((uintptr_t) src & 15) == 0 && ((size_t) k * (size_t) m_elem) % 16 == 0) ? 1 : 0;
+        a.src_tma = (((uintptr_t) src & 15) == 0 && ((size_t) k * (size_t) m_elem) % 16 == 0 && ((size_t) ld * (size_t) m_elem) % 16 == 0) ? 1 : 0;
+        a.src_ld = ld;
+        a.dst_ld = ld;
         a.slab = (const unsigned char *) s.slab;
         a.tasks = (const SweepTask *) s.tasks;
         a.done = (int *) s.done;
@@ -547,7 +575,7 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst) {
     cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, block, 1, 1, (unsigned) smem, nullptr, params));
 }
 
-void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst) {
+void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst, int ld) {
     const SweepDev &s = m_sweep[upper ? 1 : 0];
     char name[64];
     // the tracing kernels (CHB_TRACE=1) also carry the experiment switches of CHB_FRONT_DEBUG
@@ -572,8 +600,10 @@ void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst) {
         a.epoch = m_epoch;
         a.ring_rows = ring_rows;
         a.page_bytes = s.page_bytes;
-        a.src_tma = (((uintptr_t) src & 15) == 0 && ((size_t) k * (size_t) m_elem) % 16 == 0) ? 1 : 0;
-        a.dst_vec = (((uintptr_t) dst & 15) == 0 && k % 4 == 0) ? 1 : 0;
+        a.src_tma = (((uintptr_t) src & 15) == 0 && ((size_t) k * (size_t) m_elem) % 16 == 0 && ((size_t) ld * (size_t) m_elem) % 16 == 0) ? 1 : 0;
+        a.dst_vec = (((uintptr_t) dst & 15) == 0 && k % 4 == 0 && ((size_t) ld * (size_t) m_elem) % 16 == 0) ? 1 : 0;
+        a.src_ld = ld;
+        a.dst_ld = ld;
         a.debug = 0;
         if (const char *v = std::getenv("CHB_FRONT_DEBUG")) a.debug = std::atoi(v);
         a.slab = (const unsigned char *) s.slab;
@@ -612,7 +642,10 @@ int GpuSolver::device_error() {
     return word;
 }
 
-void GpuSolver::solve(int k, const void *b, void *x) {
+void GpuSolver::solve(int k, const void *b, void *x, int ld_b, int ld_x) {
+    if (ld_b <= 0) ld_b = k;
+    if (ld_x <= 0) ld_x = k;
+    if (ld_b < k || ld_x < k) throw std::invalid_argument("row stride smaller than the number of RHS columns");
     if (k != m_k) {
         if (k > 128) throw std::invalid_argument("The number of RHS should be less than 128.");
         if (k < 1) throw std::invalid_argument("The number of RHS should be at least 1.");
@@ -644,11 +677,11 @@ void GpuSolver::solve(int k, const void *b, void *x) {
     }
     m_epoch += 1;
     if (m_front) {
-        front_sweep(false, k, b, nullptr);  // tmp = L^-1 P b
-        front_sweep(true, k, nullptr, x);   // x = P' L^-T tmp
+        front_sweep(false, k, b, nullptr, ld_b);  // tmp = L^-1 P b
+        front_sweep(true, k, nullptr, x, ld_x);   // x = P' L^-T tmp
     } else {
-        sweep(false, k, b, nullptr);
-        sweep(true, k, nullptr, x);
+        sweep(false, k, b, nullptr, ld_b);
+        sweep(true, k, nullptr, x, ld_x);
     }
 }
 
@@ -656,19 +689,37 @@ void GpuSolver::solve(int k, const void *b, void *x) {
 // four) blocks: the strided H2D copy of block c + 1 (copy stream), the two sweeps of block c (legacy stream) and the
 // D2H copy of block c - 1 (second copy stream) overlap; events order them.  PCIe then runs in both directions
 // while the sweeps execute.
+bool GpuSolver::wide_rhs_allowed() {
+    const char *v = std::getenv("CHB_ALLOW_WIDE_RHS");
+    return v && std::atoi(v) != 0;
+}
+
+void GpuSolver::solve_wide(int k, const void *b, void *x, int ld_b, int ld_x) {
+    if (ld_b <= 0) ld_b = k;
+    if (ld_x <= 0) ld_x = k;
+    if (k <= 128) return solve(k, b, x, ld_b, ld_x);
+    if (!wide_rhs_allowed()) throw std::invalid_argument("The number of RHS should be less than 128.");
+    for (int c0 = 0; c0 < k; c0 += 128) {  // panels of 128 columns: 512-byte (f32) column offsets, the sweeps' full width
+        const int kc = std::min(128, k - c0);
+        solve(kc, (const char *) b + (size_t) m_elem * (size_t) c0, (char *) x + (size_t) m_elem * (size_t) c0, ld_b, ld_x);
+    }
+}
+
 void GpuSolver::solve_host(int k, const void *b_host, void *x_host) {
-    if (k > 128) throw std::invalid_argument("The number of RHS should be less than 128.");
+    if (k > 128 && !wide_rhs_allowed()) throw std::invalid_argument("The number of RHS should be less than 128.");
     if (k < 1) throw std::invalid_argument("The number of RHS should be at least 1.");
     const size_t es = (size_t) m_elem;
     const size_t bytes = es * (size_t) m_n * (size_t) k;
     int n_blocks = k >= 64 ? 2 : 1;  // measured on cfg4: 2 blocks of 64 columns beat 4 of 32 (a sweep is latency-bound, not k-bound)
     if (const char *v = std::getenv("CHB_HOST_BLOCKS")) n_blocks = std::max(1, std::min(std::min(4, k), std::atoi(v)));
-    const int kb = (k + n_blocks - 1) / n_blocks;
+    n_blocks = std::max(n_blocks, (k + 127) / 128);  // a block is one solve: at most 128 columns
+    const int kb = ((k + n_blocks - 1) / n_blocks + 3) & ~3;
     {
         ContextGuard guard(m_dev);
         if (bytes > m_stage_bytes) {
             dev_free(m_stage_b);
             dev_free(m_stage_x);
+            m_stage_bytes = 0;
             m_stage_b = dev_alloc(bytes);
             m_stage_x = dev_alloc(bytes);
             m_stage_bytes = bytes;
@@ -677,10 +728,13 @@ void GpuSolver::solve_host(int k, const void *b_host, void *x_host) {
         if (n_blocks > 1 && !m_copy_in) {
             cuda_check(cuStreamCreate(&m_copy_in, 1));   // CU_STREAM_NON_BLOCKING: no implicit sync with the legacy stream
             cuda_check(cuStreamCreate(&m_copy_out, 1));
-            for (int i = 0; i < 4; ++i) {
-                cuda_check(cuEventCreate(&m_ev_in[i], 2));   // CU_EVENT_DISABLE_TIMING
-                cuda_check(cuEventCreate(&m_ev_out[i], 2));
-            }
+        }
+        while ((int) m_ev_in.size() < n_blocks) {
+            CUevent a = nullptr, c = nullptr;
+            cuda_check(cuEventCreate(&a, 2));   // CU_EVENT_DISABLE_TIMING
+            cuda_check(cuEventCreate(&c, 2));
+            m_ev_in.push_back(a);
+            m_ev_out.push_back(c);
         }
     }
     if (n_blocks == 1) {

@@ -80,7 +80,14 @@ public:
 
     // Enqueues forward + backward sweeps on the legacy default stream; b, x: (n, k) row-major
     // device arrays of the solver's element type.  Throws std::invalid_argument for k > 128.
-    void solve(int k, const void *b, void *x);
+    // ld_b / ld_x: elements between consecutive rows of b / x (0: k), for solving a column block of a wider array in place.
+    void solve(int k, const void *b, void *x, int ld_b = 0, int ld_x = 0);
+    // Any number of columns as panels of <= 128 (opt-in, see wide_rhs_allowed): lifts the reference's cap
+    // (src/cholesky_solver.cpp:419-420) without changing the default behaviour.
+    void solve_wide(int k, const void *b, void *x, int ld_b = 0, int ld_x = 0);
+    // CHB_ALLOW_WIDE_RHS=1 in the environment: more than 128 RHS columns are solved in column panels instead of raising
+    // the reference's "The number of RHS should be less than 128."
+    static bool wide_rhs_allowed();
     // Same, host buffers: H2D, solve, D2H, stream sync (end-to-end entry).
     void solve_host(int k, const void *b_host, void *x_host);
 
@@ -109,8 +116,8 @@ private:
     void analyze(TriangleAnalysis &t, const std::vector<int> &ptr, const std::vector<int> &idx, bool lower);
     void analyze_etree(const HostFactor &L);
     void upload_sweep(SweepDev &d, const SweepImage &img);
-    void sweep(bool upper, int k, const void *src, void *dst);
-    void front_sweep(bool upper, int k, const void *src, void *dst);
+    void sweep(bool upper, int k, const void *src, void *dst, int ld);
+    void front_sweep(bool upper, int k, const void *src, void *dst, int ld);
     void upload_front(SweepDev &d, const FrontImage &img);
 
     DeviceState *m_dev = nullptr;
@@ -140,7 +147,7 @@ private:
     void *m_stage_b = nullptr, *m_stage_x = nullptr;
     size_t m_stage_bytes = 0;
     CUstream m_copy_in = nullptr, m_copy_out = nullptr;
-    CUevent m_ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, m_ev_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<CUevent> m_ev_in, m_ev_out;  // one pair per column block
 };
 
 }  // namespace chb

@@ -44,6 +44,7 @@ struct SweepArgs {
     int local_rows;       // largest local task (informational; local tasks live in the row ring)
     int ring_rows;        // rows of the shared-memory row ring (>= largest local task + 32)
     int src_tma;          // rows of the user's b can be fetched by TMA (16-byte aligned, 16-byte multiples)
+    int src_ld, dst_ld;   // elements between consecutive rows of b / x (== k unless a column block of a wider array is solved)
     const unsigned char *slab;
     const SweepTask *tasks;     // ticket-ordered
     int *done;            // per-task epoch flags
@@ -68,6 +69,7 @@ struct FrontArgs {
     int page_bytes;       // slab page size (front_schedule.h: front_page_bytes)
     int src_tma;          // rows of the user's b can be fetched by TMA (16-byte aligned, 16-byte multiples)
     int dst_vec;          // rows of the user's x can be written with vector stores
+    int src_ld, dst_ld;   // elements between consecutive rows of b / x (== k unless a column block of a wider array is solved)
     int debug;            // timing experiments only (CHB_FRONT_DEBUG): bits skip LROWS / LSTORE / BAR / MMA / ASM / EPI bodies (results invalid)
     const unsigned char *slab;
     const SweepTask *tasks;     // ticket-ordered; `level` = task id = index of its ready flag

@@ -97,8 +97,14 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 // A waiting warp is suspended by the hardware (up to the hint) instead of spinning through the issue slots of the
 // working warps on its scheduler: spin instructions were 12 % of everything issued on cfg4 before (ncu).
 constexpr uint32_t kSuspendHintNs = 20000;
+__device__ __forceinline__ unsigned long long global_ns();
+// Watchdog of every wait: 20 s of %globaltimer, not an attempt count (the suspend hint is an upper bound, so a count
+// is a budget of anything between milliseconds and minutes: a debugger, compute-sanitizer or a pre-empted context
+// must not trip it).  A dependency that never arrives is a schedule or kernel bug: trap rather than hang the GPU.
+constexpr unsigned long long kWatchdogNs = 20ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     unsigned spins = 0;
+    unsigned long long t0 = 0;
     for (;;) {
         uint32_t ok;
         asm volatile(
@@ -111,7 +117,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
             : "memory");
         if (ok) return;
-        if (++spins > (1u << 22)) __trap();
+        if ((++spins & 255u) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kWatchdogNs) __trap();
+        }
     }
 }
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
@@ -202,8 +212,12 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 // Spin loops trap instead of hanging the GPU if a dependency never arrives (a schedule or kernel bug).
-#define SWEEP_SPIN_GUARD(counter)            \
-    if (++(counter) > (1u << 27)) __trap();
+#define SWEEP_SPIN_GUARD(counter)                                                          \
+    if ((++(counter) & 0xffffu) == 0) {                                                    \
+        const unsigned long long guard_now = global_ns();                                  \
+        if (guard_t0 == 0) guard_t0 = guard_now;                                           \
+        if (guard_now - guard_t0 > kWatchdogNs) __trap();                                  \
+    }
 
 // A task descriptor in the CTA's shared-memory task queue (loader -> compute warps).
 struct QueuedTask {
@@ -330,7 +344,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
     auto copy_rhs_rows = [&](const int *perm, int n) -> uint32_t {
         if (src_tma) {
             for (int i = lane; i < n; i += 32)
-                tma_load_1d(sm.ring + (size_t) (head + i) * kp, a.src + (size_t) perm[i] * k, src_row_bytes,
+                tma_load_1d(sm.ring + (size_t) (head + i) * kp, a.src + (size_t) perm[i] * a.src_ld, src_row_bytes,
                             sm.rfull + j_issue % kRowBars);
             return (uint32_t) n * src_row_bytes;
         }
@@ -338,7 +352,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
 #pragma unroll 1
         for (int e = lane; e < total; e += 32) {
             const int i = e / k, c = e - i * k;
-            sm.ring[(size_t) (head + i) * kp + c] = __ldg(a.src + (size_t) perm[i] * k + c);
+            sm.ring[(size_t) (head + i) * kp + c] = __ldg(a.src + (size_t) perm[i] * a.src_ld + c);
         }
         return 0u;
     };
@@ -478,12 +492,14 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     for (int e = lane; e < n_wait; e += 32) {
                         const int *flag = a.done + (waits[e] - 1);
                         unsigned spins = 0;
+                        unsigned long long guard_t0 = 0;
                         while (ld_acquire_gpu(flag) != epoch) { SWEEP_SPIN_GUARD(spins) }
                     }
                     __syncwarp();
                 } else {
                     // poll: one flag per lane, the ready prefix goes now
                     unsigned spins = 0;
+                    unsigned long long guard_t0 = 0;
                     for (;;) {
                         bool ready = true;
                         if (lane < n && my_code != 0) ready = ld_acquire_gpu(a.done + (my_code - 1)) == epoch;
@@ -493,6 +509,8 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                         SWEEP_SPIN_GUARD(spins)
                     }
                 }
+                // the producers' rows were written with generic-proxy stores and are read through the async proxy (TMA) below
+                asm volatile("fence.proxy.async;" ::: "memory");
                 const unsigned char *last = p;
                 for (int i = 0; i < n_go; ++i) {
                     const unsigned char *rec = p + __shfl_sync(kFullMask, my_off, i);
@@ -555,6 +573,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     }
                     if (n_copy > 0) copy_rows(slot, from, n_copy, bar);
                     if (rhs_n > 0) tx = copy_rhs_rows(rhs_perm, rhs_n);
+                    if (rhs_n > 0 && !src_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes to ring rows TMA reuses later
                     __syncwarp();  // manual copies (unaligned right-hand side) are complete before the arrival
                     if (lane == 0) mbar_expect_tx(bar, tx);
                     j_issue += 1;
@@ -631,6 +650,8 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
             return head;
         };
         auto release_rows = [&](int nr) {
+            // ring rows written with generic stores (local tasks) are overwritten by TMA once released
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.rempty + j % kRowBars);
             j += 1;
@@ -729,7 +750,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         for (int i = 0; i < W; ++i) {
                             if (i < w) {
                                 __stcg(out + (size_t) i * kp, T[i]);
-                                if (scatter) a.dst[(size_t) perm[i] * k + col] = T[i];
+                                if (scatter) a.dst[(size_t) perm[i] * a.dst_ld + col] = T[i];
                             }
                         }
                     }
@@ -743,7 +764,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                         for (int i = 0; i < n_int; ++i) {
                             const F v = ring_at(lbase, i);
                             __stcg(a.tmp + (size_t) (lo + i) * kp + col, v);
-                            if (UPPER) a.dst[(size_t) perm[i] * k + col] = v;
+                            if (UPPER) a.dst[(size_t) perm[i] * a.dst_ld + col] = v;
                         }
                         // forward: the task's contributions to its ancestors' rows (local rows n_int ...) -> contribution buffer
                         if (!UPPER) {

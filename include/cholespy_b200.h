@@ -76,6 +76,17 @@ int chb_solver_solve_cuda(chb_solver *s, int n_rhs, const void *b_dev, void *x_d
 int chb_solver_solve_host(chb_solver *s, int n_rhs, const void *b_host, void *x_host);
 /* CHOLMOD solve on the host for CPU-mode solvers.  Replaces solve_cpu (src/cholesky_solver.cpp:434-463). */
 int chb_solver_solve_cpu(chb_solver *s, int n_rhs, const void *b, void *x);
+/* Multi-GPU inside the solve call (single process; new: the reference is single-device, src/cuda_driver.cpp:124-125).
+ * `devices` = ordinals of n_devices ADDITIONAL B200s: the device image is replicated to them once (ncclBroadcast over
+ * NVLink, peer copies where libnccl is absent), and every later chb_solver_solve_cuda with enough columns splits them
+ * into contiguous blocks, one per device: the solver's own device works in place in b / x, the others get their block
+ * by a strided peer copy, and the legacy stream of the solver's device is joined to all of them before the call
+ * returns (same asynchronous semantics as the unsharded call).  n_devices = 0 undoes it.  The environment variable
+ * CHB_SHARD_GPUS=N does the same for every CUDA-mode solver at construction (N visible devices), so an unchanged
+ * cholespy program uses them.  chb_solver_shard_info: devices in use, replication (0 none, 1 nccl, 2 peer copies),
+ * bytes replicated per device, microseconds it took. */
+int chb_solver_shard(chb_solver *s, int n_devices, const int32_t *devices);
+int chb_solver_shard_info(const chb_solver *s, int64_t *out, int cap);
 /* Blocks until the device is idle and reports whether the sweep kernels' watchdog fired (a task dependency that
  * never arrived: CHB_ERR_RUNTIME).  New: the reference's kernels spin forever in that case
  * (kernels/kernels.cu:96-98). */

@@ -51,7 +51,9 @@ def main():
     if key and traffic:
         path = os.path.join(os.path.dirname(os.path.abspath(out)), "ncu_traffic.json")
         table = json.load(open(path)) if os.path.exists(path) else {}
-        table[key] = sum(traffic) / len(traffic)
+        gi = hdr.index("launch__grid_size")
+        table[key] = {"bytes_per_launch": sum(traffic) / len(traffic), "grid": int(float(data[0][gi])),
+                      "kernels": data[0][name_i].split("(")[0], "source": "profiles/" + os.path.basename(out)}
         json.dump(table, open(path, "w"), indent=1, sort_keys=True)
 
 

@@ -1,5 +1,7 @@
 """GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
 (cholespy_b200's Python mirror is a ctypes binding of include/cholespy_b200.h)."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -375,3 +377,180 @@ def test_analysis_row_kernel_matches_etree_kernel(oracle_mod, native_lib, monkey
             lb, ob = b.analysis(lower)
             assert np.array_equal(la, lb) and np.array_equal(oa, ob)
         assert a.info()["n_levels_lower"] == b.info()["n_levels_lower"] and a.info()["n_levels_upper"] == b.info()["n_levels_upper"]
+
+
+# ------------------------------------------------------------------------------------------------
+# Round 2: opt-in wide RHS, in-API multi-GPU sharding, disk cache, foreign array protocols, full-size configs
+# ------------------------------------------------------------------------------------------------
+def test_wide_rhs_is_opt_in(monkeypatch):
+    """More than 128 columns: the reference's ValueError by default (tests/test_cholesky.py:42-44), column panels of
+    128 with CHB_ALLOW_WIDE_RHS=1 -- every column then equals the same column solved in a narrow call, bit for bit."""
+    p = problems.build_problem("ico4")
+    s = _solver(p, np.float32)
+    b = np.random.default_rng(7).random((p["n"], 300)).astype(np.float32)
+    bt = torch.tensor(b, device="cuda")
+    xt = torch.zeros_like(bt)
+    with pytest.raises(ValueError, match="The number of RHS should be less than 128."):
+        s.solve(bt, xt)
+    monkeypatch.setenv("CHB_ALLOW_WIDE_RHS", "1")
+    s.solve(bt, xt)
+    torch.cuda.synchronize()
+    x = xt.cpu().numpy()
+    for c0 in (0, 128, 256):
+        kc = min(128, 300 - c0)
+        assert np.array_equal(x[:, c0:c0 + kc], _gpu_solve(s, np.ascontiguousarray(b[:, c0:c0 + kc])))
+    A = problems.to_scipy_csc(p)
+    assert rel_residual(A, x, b) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sharded_solve_over_gpus(dtype, oracle_mod, native_lib):
+    """chb_solver_shard: 128 columns through .solve(b, x) over every visible GPU equal the single-GPU result bit for bit
+    (columns are independent and each is solved by the same kernels), b untouched, k = 1..3 stay on one device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    p = problems.build_problem("ico5")
+    s = _solver(p, dtype, device="cuda:0")
+    rng = np.random.default_rng(8)
+    b = rng.random((p["n"], 128)).astype(dtype)
+    x_one = _gpu_solve(s, b)
+    s.shard(list(range(1, torch.cuda.device_count())))
+    info = s.shard_info()
+    assert info["devices"] == torch.cuda.device_count() and info["replication"] in ("nccl", "peer") and info["bytes"] > 0
+    for k in (128, 100, 64, 17, 3, 1):
+        bk = np.ascontiguousarray(b[:, :k])
+        assert np.array_equal(_gpu_solve(s, bk), x_one[:, :k]), k
+    for _ in range(3):  # repeated solves reuse the staging buffers and events
+        assert np.array_equal(_gpu_solve(s, b), x_one)
+    s.shard([])
+    assert s.shard_info()["devices"] == 1
+    assert np.array_equal(_gpu_solve(s, b), x_one)
+
+
+def test_shard_from_environment(monkeypatch):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    p = problems.build_problem("ico4")
+    plain = _solver(p, np.float32)
+    monkeypatch.setenv("CHB_SHARD_GPUS", "2")
+    sharded = _solver(p, np.float32)
+    assert sharded.shard_info()["devices"] == 2 and plain.shard_info()["devices"] == 1
+    b = np.random.default_rng(9).random((p["n"], 64)).astype(np.float32)
+    assert np.array_equal(_gpu_solve(sharded, b), _gpu_solve(plain, b))
+
+
+def test_arrays_on_another_gpu_are_rejected():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    p = problems.build_problem("cube")
+    s = _solver(p, np.float32, device="cuda:0")
+    b = torch.zeros((p["n"], 2), dtype=torch.float32, device="cuda:1")
+    with pytest.raises(ValueError, match="solver's device"):
+        s.solve(b, torch.zeros_like(b))
+
+
+def test_disk_cache_of_factor_and_images(tmp_path, monkeypatch):
+    """CHB_CACHE_DIR: the second constructor of the same matrix reads the factor and both sweep images back and solves
+    to the same bits; for both image kinds."""
+    p = problems.build_problem("ico5")
+    b = np.random.default_rng(10).random((p["n"], 9)).astype(np.float32)
+    for mode in ("panel", "front"):
+        monkeypatch.setenv("CHB_SWEEP", mode)
+        monkeypatch.delenv("CHB_CACHE_DIR", raising=False)
+        x0 = _gpu_solve(_solver(p, np.float32), b)
+        monkeypatch.setenv("CHB_CACHE_DIR", str(tmp_path / mode))
+        s1 = _solver(p, np.float32)
+        names = sorted(f.name.split("_")[0] for f in (tmp_path / mode).iterdir())
+        assert names == sorted(["factor", mode])
+        s2 = _solver(p, np.float32)
+        assert s1.info() == s2.info()
+        assert np.array_equal(_gpu_solve(s1, b), x0) and np.array_equal(_gpu_solve(s2, b), x0)
+        assert np.array_equal(s2.analysis(True)[0], s1.analysis(True)[0])
+
+
+class _CudaArrayInterface:
+    """A foreign CUDA array: exposes only __cuda_array_interface__ (what cupy / numba arrays offer)."""
+
+    def __init__(self, t):
+        self._t = t
+        self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+
+class _DLPackOnly:
+    """A foreign array that offers only the DLPack protocol (what jax / tensorflow arrays offer)."""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __dlpack__(self, stream=None):
+        return self._t.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+# Mirrors reference tests/test_cholesky.py:88-199 (test_frameworks): arrays of other frameworks reach the solver through
+# __cuda_array_interface__ / DLPack; none of those frameworks is installed here, so the protocols are exercised directly.
+@pytest.mark.parametrize("wrap", [_CudaArrayInterface, _DLPackOnly])
+def test_foreign_array_protocols(wrap):
+    np.random.seed(45)
+    n_verts, faces = problems.icosphere(3)
+    values, idx = problems.mesh_laplacian_coo(n_verts, faces, 2.0)
+    b = np.random.random(size=(n_verts, 32)).astype(np.float32)
+    x_ref = spsolve(sp.csc_matrix((values, idx)), b)
+    to = lambda a: wrap(torch.tensor(a, device="cuda"))  # noqa: E731
+    solver = CholeskySolverF(n_verts, to(idx[0].astype(np.int32)), to(idx[1].astype(np.int32)), to(values), MatrixType.COO)
+    bt = torch.tensor(b, device="cuda")
+    xt = torch.zeros_like(bt)
+    solver.solve(wrap(bt), wrap(xt))
+    torch.cuda.synchronize()
+    assert np.allclose(xt.cpu().numpy(), x_ref)
+
+
+def _full_size_check(name, dtype, k, native_lib, cache):
+    """A BASELINE.json config at FULL size: residual against the matrix, agreement with the reference's CHOLMOD solve on
+    a column sample when oracle/_ref is present, and size-independent properties (linearity, determinism)."""
+    import time
+    p = problems.build_problem(name)
+    os.environ["CHB_CACHE_DIR"] = cache
+    try:
+        t = time.time()
+        s = _solver(p, dtype)
+        print("%s: constructor %.1f s" % (name, time.time() - t))
+    finally:
+        del os.environ["CHB_CACHE_DIR"]
+    A = problems.to_scipy_csc(p)
+    rng = np.random.default_rng(11)
+    b = rng.random((p["n"], k)).astype(dtype)
+    x = _gpu_solve(s, b)
+    assert rel_residual(A, x, b) < (2e-5 if dtype == np.float32 else 1e-12), name
+    assert np.array_equal(_gpu_solve(s, b), x), "not deterministic"
+    # linearity: A^-1 (2 b) = 2 A^-1 b exactly (scaling by a power of two commutes with every rounding)
+    assert np.array_equal(_gpu_solve(s, 2 * b), 2 * x)
+    return s, p, b, x
+
+
+def test_full_size_cfg2(native_lib, tmp_path, oracle_mod):
+    """configs[1]: icosphere(8), I + 10 L, CholeskySolverF, 3 RHS."""
+    import os
+    s, p, b, x = _full_size_check("cfg2", np.float32, 3, native_lib, str(tmp_path))
+    if oracle_mod.reference_available():
+        ref = oracle_mod.ReferenceSolver(p["n"], p["ii"], p["jj"], p["x"], p["fmt"], np.float32, cpu=True)
+        xc = ref.solve_cpu(b)
+        ref.close()
+        assert max_rel_err(x, xc) < 1e-5
+
+
+def test_full_size_cfg5_stand_in(native_lib, tmp_path):
+    """configs[4] (locality-structured stand-in): n = 10^6, CSR input, CholeskySolverD, 128 RHS."""
+    _full_size_check("cfg5", np.float64, 128, native_lib, str(tmp_path))
+
+
+def test_deep_levels_single_rhs(native_lib, tmp_path):
+    """configs[2] shape at a size CHOLMOD factorises in seconds (3-D 7-point Laplacian 40^3, CSC, CholeskySolverD, 1 RHS:
+    deep level sets, latency-bound); CHB_FULL_SIZE=1 adds the 64^3 stand-in (5 minutes of CHOLMOD) and cfg4."""
+    import os
+    _full_size_check("grid3d-40", np.float64, 1, native_lib, str(tmp_path))
+    if os.environ.get("CHB_FULL_SIZE"):
+        _full_size_check("cfg3", np.float64, 1, native_lib, str(tmp_path))
+        _full_size_check("cfg4", np.float32, 128, native_lib, str(tmp_path))

@@ -142,3 +142,44 @@ def test_intake_sums_duplicates_and_orders_entries(native_lib):
     x = np.zeros_like(b)
     solver.solve(b, x)
     assert np.allclose(x, spsolve(A.tocsc(), b), rtol=1e-10, atol=1e-12)
+
+
+def test_malformed_pointer_arrays_are_rejected(native_lib):
+    """A CSR/CSC pointer array that is not monotone or does not end at nnz must raise, not index out of bounds."""
+    n_verts, faces = problems.cube()
+    values, idx = problems.mesh_laplacian_coo(n_verts, faces, 2.0)
+    A = sp.csc_matrix((values, idx))
+    bad = A.indptr.astype(np.int32).copy()
+    bad[3] = bad[5] + 1
+    with pytest.raises(ValueError, match="invalid pointer array"):
+        CholeskySolverD(n_verts, bad, A.indices.astype(np.int32), A.data, MatrixType.CSC)
+    bad = A.indptr.astype(np.int32).copy()
+    bad[0] = 1
+    with pytest.raises(ValueError, match="invalid pointer array"):
+        CholeskySolverD(n_verts, bad, A.indices.astype(np.int32), A.data, MatrixType.CSR)
+
+
+def test_factor_disk_cache(native_lib, tmp_path, monkeypatch):
+    """CHB_CACHE_DIR: the second factorisation of the same matrix is read back from disk (same bytes), a different
+    matrix gets its own entry, and without the variable nothing is written."""
+    from helpers import factorize
+    p = problems.build_problem("ico3")
+    first = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    assert not list(tmp_path.iterdir())
+    monkeypatch.setenv("CHB_CACHE_DIR", str(tmp_path))
+    a = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    files = sorted(f.name for f in tmp_path.iterdir())
+    assert len(files) == 1 and files[0].startswith("factor_")
+    b = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])   # cache hit
+    for u, v, w in zip(first, a, b):
+        assert np.array_equal(u, v) and np.array_equal(u, w)
+    # a corrupted entry is ignored (and replaced), never trusted
+    path = tmp_path / files[0]
+    path.write_bytes(path.read_bytes()[:100])
+    c = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    for u, v in zip(first, c):
+        assert np.array_equal(u, v)
+    x2 = p["x"].copy()
+    x2[-1] += 1.0
+    factorize(native_lib, p["n"], p["ii"], p["jj"], x2, p["fmt"])
+    assert len(list(tmp_path.iterdir())) == 2
