@@ -2,6 +2,7 @@
 #include "gpu_solver.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -152,7 +153,7 @@ void ImageShape::to_words(int64_t *w) const {
     w[15] = n_contrib_rows;
     w[16] = front;
     for (int u = 0; u < 2; ++u) w[17 + u] = n_w_rows[u], w[19 + u] = max_stage_rows[u];
-    w[21] = n_warps, w[22] = page_bytes, w[23] = 0;
+    w[21] = n_warps, w[22] = page_bytes, w[23] = local_rows_cap[0] | local_rows_cap[1] << 16;
 }
 ImageShape ImageShape::from_words(const int64_t *w) {
     ImageShape s;
@@ -167,6 +168,7 @@ ImageShape ImageShape::from_words(const int64_t *w) {
     s.front = w[16];
     for (int u = 0; u < 2; ++u) s.n_w_rows[u] = w[17 + u], s.max_stage_rows[u] = w[19 + u];
     s.n_warps = w[21], s.page_bytes = w[22];
+    s.local_rows_cap[0] = w[23] & 0xffff, s.local_rows_cap[1] = w[23] >> 16 & 0xffff;
     return s;
 }
 
@@ -210,6 +212,17 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
     // 8 while at least kWideLevel tasks of the same dependency level are still to be handed out, else 1
     size_t kWideLevel = 16384;
     if (const char *v = std::getenv("CHB_WIDE_LEVEL")) kWideLevel = (size_t) std::max(1, std::atoi(v));
+    // selection rule of the local-task kernel: CHB_LOCAL_KERNEL=0 leaves every task to the persistent kernel (the
+    // round-1 behaviour); CHB_LOCAL_KERNEL_ROWS="fwd,bwd" / CHB_LOCAL_KERNEL_BYTES: the per-warp budget
+    const bool upper = &d == &m_sweep[1];
+    bool use_local = true;
+    int rows_cap = upper ? 44 : 28, bytes_cap = 3584;
+    if (const char *v = std::getenv("CHB_LOCAL_KERNEL")) use_local = std::atoi(v) != 0;
+    if (const char *v = std::getenv("CHB_LOCAL_KERNEL_ROWS")) {
+        int f = 0, b = 0;
+        if (std::sscanf(v, "%d%*[,:]%d", &f, &b) == 2) rows_cap = std::max(1, std::min(255, upper ? b : f));
+    }
+    if (const char *v = std::getenv("CHB_LOCAL_KERNEL_BYTES")) bytes_cap = std::max(256, std::atoi(v));
     const size_t nt = img.order.size();
     size_t level_end = 0;
     for (size_t t = 0; t < nt; ++t) {
@@ -222,10 +235,52 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
         by_ticket[t] = src;
         by_ticket[t].level = (uint32_t) img.order[t];
         by_ticket[t].bytes |= (level_end - t >= kWideLevel ? 7u : 0u) << 28;
+        // bit 31: a local task the local-task kernel takes (local_sweep.cuh): one whose rows and records fit that
+        // kernel's shared-memory budget per warp; the few larger ones stay with the persistent kernel
+        uint32_t head[4] = {0, 0, 0, 0};
+        std::memcpy(head, img.slab.data() + src.offset, sizeof head);
+        if (use_local && (head[0] & 0x3fu) == (uint32_t) REC_LOCAL_LOAD) {
+            const int n_int = (int) (head[2] & 0xffffu), n_ext = (int) (head[2] >> 16);
+            const int rows = upper ? n_int + n_ext : n_int;   // forward contributions go straight to global memory
+            if (rows <= rows_cap && (int) src.bytes <= bytes_cap) by_ticket[t].bytes |= 1u << 31;
+        }
     }
+    d.local_rows_cap = rows_cap;
     h2d(d.slab, img.slab.data(), img.slab.size());
     h2d(d.tasks, by_ticket.data(), sizeof(TaskDesc) * by_ticket.size());
     sync0();
+    split_tasks(d, by_ticket.data());
+}
+
+// The persistent kernel's and the local-task kernel's task tables, derived from the replicated one (replicas
+// receive `tasks` from a peer and derive theirs on first use).
+void GpuSolver::split_tasks(SweepDev &s, const void *host_tasks) {
+    std::vector<TaskDesc> all((size_t) s.n_tasks);
+    if (host_tasks) {
+        std::memcpy(all.data(), host_tasks, sizeof(TaskDesc) * all.size());
+    } else {
+        d2h(all.data(), s.tasks, sizeof(TaskDesc) * all.size());
+        sync0();
+    }
+    std::vector<TaskDesc> main_t, local_t;
+    uint32_t cap = 0;
+    for (const TaskDesc &t : all) {
+        if (t.bytes >> 31) {
+            local_t.push_back(t);
+            cap = std::max(cap, t.bytes & 0x0fffffffu);
+        } else {
+            main_t.push_back(t);
+        }
+    }
+    s.n_main = (int) main_t.size();
+    s.n_local = (int) local_t.size();
+    s.local_slab_cap = (int) ((cap + 15u) & ~15u);
+    s.main_tasks = dev_alloc(sizeof(TaskDesc) * std::max<size_t>(main_t.size(), 1));
+    s.local_tasks = dev_alloc(sizeof(TaskDesc) * std::max<size_t>(local_t.size(), 1));
+    if (!main_t.empty()) h2d(s.main_tasks, main_t.data(), sizeof(TaskDesc) * main_t.size());
+    if (!local_t.empty()) h2d(s.local_tasks, local_t.data(), sizeof(TaskDesc) * local_t.size());
+    sync0();
+    s.split = true;
 }
 
 void GpuSolver::upload_front(SweepDev &d, const FrontImage &img) {
@@ -446,6 +501,7 @@ GpuSolver::GpuSolver(int device, int elem_size, const ImageShape &shape)
         m_sweep[u].n_slots = (int) shape.n_slots[u];
         m_sweep[u].n_task_levels = (int) shape.n_task_levels[u];
         m_sweep[u].max_local_rows = (int) shape.max_local_rows[u];
+        m_sweep[u].local_rows_cap = (int) shape.local_rows_cap[u];
         m_sweep[u].n_w_rows = shape.n_w_rows[u];
         m_sweep[u].max_stage_rows = (int) shape.max_stage_rows[u];
         m_sweep[u].page_bytes = (int) shape.page_bytes;
@@ -469,6 +525,8 @@ GpuSolver::~GpuSolver() {
         dev_free(s.tasks);
         dev_free(s.done);
         dev_free(s.trace);
+        dev_free(s.main_tasks);
+        dev_free(s.local_tasks);
     }
     dev_free(m_counters);
     dev_free(m_tmp);
@@ -497,6 +555,7 @@ ImageShape GpuSolver::shape() const {
         s.n_slots[u] = m_sweep[u].n_slots;
         s.n_task_levels[u] = m_sweep[u].n_task_levels;
         s.max_local_rows[u] = m_sweep[u].max_local_rows;
+        s.local_rows_cap[u] = m_sweep[u].local_rows_cap;
     }
     s.exact_order = m_exact ? 1 : 0;
     s.n_contrib_rows = m_sweep[0].n_contrib_rows;
@@ -519,9 +578,77 @@ std::vector<ImageBuffer> GpuSolver::image() const {
     return out;
 }
 
-void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
+// columns a lane of the local-task kernel owns: the smallest of 1, 2, 4 (f64: 1, 2) that covers k with one warp
+static int local_cpl(int elem, int k) {
+    const int kp = (k + 3) & ~3, cap = elem == 4 ? 4 : 2;
+    int cpl = 1;
+    while (cpl < cap && 32 * cpl < kp) cpl *= 2;
+    return cpl;
+}
+
+// The local tasks of one sweep as a plain launch (local_sweep.cuh).  False (nothing launched) when there are none
+// or when the largest one does not fit an SM's shared memory: the caller then leaves them to the persistent kernel.
+bool GpuSolver::local_sweep(bool upper, int k, const void *src, void *dst, int ld, bool probe_only) {
+    const SweepDev &s = m_sweep[upper ? 1 : 0];
+    if (s.n_local == 0) return false;
+    const int cpl = local_cpl(m_elem, k);
+    const size_t smem = 2 * (size_t) s.local_slab_cap + (size_t) s.local_rows_cap * 32 * (size_t) cpl * (size_t) m_elem;
+    if (smem > (size_t) 200 * 1024) return false;
+    if (probe_only) return true;
     char name[64];
-    snprintf(name, sizeof name, "chb_sweep_%s_%s%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower", m_exact ? "_exact" : "");
+    snprintf(name, sizeof name, "chb_local_%s_c%d_%s%s", m_elem == 4 ? "f32" : "f64", cpl, upper ? "upper" : "lower", m_exact ? "_exact" : "");
+    CUfunction fn = kernel(m_dev, name);
+    if (!fn) throw std::runtime_error(driver_error_text());
+    cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
+    cuda_check(cuFuncSetAttribute(fn, kFuncAttrSharedCarveout, 100));
+    const size_t vec_bytes = (size_t) cpl * (size_t) m_elem;
+    auto fill = [&](auto &a) {
+        using A = std::remove_reference_t<decltype(a)>;
+        using Float = std::remove_pointer_t<decltype(A::tmp)>;
+        a.n_tasks = s.n_local;
+        a.k = k;
+        a.epoch = m_epoch;
+        a.slab_cap = s.local_slab_cap;
+        a.src_vec = (((uintptr_t) src % vec_bytes) == 0 && ((size_t) ld * (size_t) m_elem) % vec_bytes == 0) ? 1 : 0;
+        a.dst_vec = (((uintptr_t) dst % vec_bytes) == 0 && ((size_t) ld * (size_t) m_elem) % vec_bytes == 0) ? 1 : 0;
+        a.src_ld = ld;
+        a.dst_ld = ld;
+        a.slab = (const unsigned char *) s.slab;
+        a.tasks = (const SweepTask *) s.local_tasks;
+        a.done = (int *) s.done;
+        a.tmp = (Float *) m_tmp;
+        a.src = (const Float *) src;
+        a.dst = (Float *) dst;
+        a.cbuf = (Float *) m_cbuf;
+    };
+    LocalArgs<float> a32;
+    LocalArgs<double> a64;
+    void *params[1];
+    if (m_elem == 4) {
+        fill(a32);
+        params[0] = &a32;
+    } else {
+        fill(a64);
+        params[0] = &a64;
+    }
+    const int n_slices = (k + 32 * cpl - 1) / (32 * cpl);
+    const long long items = (long long) s.n_local * n_slices;
+    int per_sm = max_resident_blocks(m_dev, fn, 32, smem) / std::max(1, m_dev->sm_count);
+    if (const char *cap = std::getenv("CHB_LOCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(cap)));
+    const int grid = (int) std::max<long long>(1, std::min<long long>(items, (long long) per_sm * m_dev->sm_count));
+    cuda_check(cuLaunchKernel(fn, (unsigned) grid, 1, 1, 32, 1, 1, (unsigned) smem, nullptr, params, nullptr));
+    return true;
+}
+
+void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
+    if (!m_sweep[upper ? 1 : 0].split) split_tasks(m_sweep[upper ? 1 : 0], nullptr);  // a replica's first solve
+    // local tasks: before the dependency-driven part in the forward sweep (they depend on nothing), after it in the
+    // backward sweep (nothing depends on them)
+    const bool local = local_sweep(upper, k, src, dst, ld, /*probe_only=*/true);
+    if (local && !upper) local_sweep(false, k, src, dst, ld);
+    char name[64];
+    snprintf(name, sizeof name, "chb_sweep_%s_%s%s%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower", m_exact ? "_exact" : "",
+             m_sweep[upper ? 1 : 0].trace ? "_trace" : "");
     CUfunction fn = kernel(m_dev, name);
     if (!fn) throw std::runtime_error(driver_error_text());
     const int local_rows = std::max(m_sweep[0].max_local_rows, m_sweep[1].max_local_rows);
@@ -538,7 +665,7 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
     auto fill = [&](auto &a) {
         using A = std::remove_reference_t<decltype(a)>;
         using Float = std::remove_pointer_t<decltype(A::tmp)>;
-        a.n_tasks = s.n_tasks;
+        a.n_tasks = local ? s.n_main : s.n_tasks;
         a.k = k;
         a.epoch = m_epoch;
         a.local_rows = local_rows;
@@ -547,7 +674,7 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
         a.src_ld = ld;
         a.dst_ld = ld;
         a.slab = (const unsigned char *) s.slab;
-        a.tasks = (const SweepTask *) s.tasks;
+        a.tasks = (const SweepTask *) (local ? s.main_tasks : s.tasks);
         a.done = (int *) s.done;
         a.ticket = ticket;
         a.ticket_next = ticket_next;
@@ -569,10 +696,11 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
         fill(a64);
         params[0] = &a64;
     }
-    int grid = std::max(1, std::min(s.n_tasks, max_resident_blocks(m_dev, fn, block, smem)));
+    int grid = std::max(1, std::min(local ? s.n_main : s.n_tasks, max_resident_blocks(m_dev, fn, block, smem)));
     if (const char *cap = std::getenv("CHB_SWEEP_CTAS_PER_SM")) grid = std::max(1, std::min(grid, std::atoi(cap) * m_dev->sm_count));
     m_last_grid = grid;
     cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, block, 1, 1, (unsigned) smem, nullptr, params));
+    if (local && upper) local_sweep(true, k, src, dst, ld);
 }
 
 void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst, int ld) {

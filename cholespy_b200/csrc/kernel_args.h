@@ -59,6 +59,24 @@ struct SweepArgs {
     unsigned long long *trace;  // optional (debug): 8 words per task {start ns, slab ready ns, end ns, cycles spent waiting, last wait ns, blocks done ns, triangle done ns, -}
 };
 
+// The local tasks of one panel sweep as a plain launch (local_sweep.cuh: chb_local_*).
+template <typename Float>
+struct LocalArgs {
+    int n_tasks;          // local tasks only
+    int k;
+    int epoch;
+    int slab_cap;         // bytes of one shared-memory record buffer (>= the largest local task, a multiple of 16)
+    int src_vec, dst_vec; // a lane's columns of a row of b / x can be moved as one vector (alignment of base and stride)
+    int src_ld, dst_ld;   // elements between consecutive rows of b / x
+    const unsigned char *slab;
+    const SweepTask *tasks;     // the local tasks, ticket order; `level` = task id = index of its ready flag
+    int *done;            // per-task epoch flags (forward: published for the persistent kernel that follows)
+    Float *tmp;           // (n, round4(k)) work vector in permuted order
+    const Float *src;     // forward: user's b
+    Float *dst;           // backward: user's x
+    Float *cbuf;          // forward contributions of the local tasks
+};
+
 // One front sweep (front_sweep.cuh: chb_front_*).  See front_schedule.h for the record format.
 template <typename Float>
 struct FrontArgs {

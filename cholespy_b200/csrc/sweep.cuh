@@ -117,11 +117,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
             : "memory");
         if (ok) return;
+#ifdef CHB_AB_COUNT_WATCHDOG
+        if (++spins > (1u << 22)) __trap();
+#else
         if ((++spins & 255u) == 0) {
             const unsigned long long now = global_ns();
             if (t0 == 0) t0 = now;
             if (now - t0 > kWatchdogNs) __trap();
         }
+#endif
     }
 }
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
@@ -510,7 +514,9 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
                     }
                 }
                 // the producers' rows were written with generic-proxy stores and are read through the async proxy (TMA) below
+#ifndef CHB_AB_NO_POLL_FENCE
                 asm volatile("fence.proxy.async;" ::: "memory");
+#endif
                 const unsigned char *last = p;
                 for (int i = 0; i < n_go; ++i) {
                     const unsigned char *rec = p + __shfl_sync(kFullMask, my_off, i);
@@ -611,7 +617,7 @@ __device__ __forceinline__ void loader_warp(const SweepArgs<F> &a, const Smem<F>
 }
 
 // ---- the compute warps -----------------------------------------------------------------------------
-template <typename F, bool UPPER, bool EXACT>
+template <typename F, bool UPPER, bool EXACT, bool TRACE>
 __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F> &sm, int warp, int lane, int n_compute) {
     const int k = a.k, kp = (k + 3) & ~3;
     const int ring_rows = a.ring_rows;
@@ -634,7 +640,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
         const int task = cur.task;
         const uint32_t total = cur.bytes;
         const uint32_t n_pages = (total + kPage - 1) / kPage;
-        if (a.trace && leader) {
+        if (TRACE && leader) {
             a.trace[8 * (size_t) task] = global_ns();
             wait_cycles = 0;
         }
@@ -643,15 +649,21 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
         int lbase = 0, lrows = 0;   // ring rows of the local task being solved
         // waits for the loader to have staged the next record's rows; returns their ring position
         auto acquire_rows = [&](int nr) {
-            const long long c0 = a.trace ? clock64() : 0;
+            const long long c0 = TRACE ? clock64() : 0;
             mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1);
-            if (a.trace) wait_cycles += clock64() - c0;
+            if (TRACE) wait_cycles += clock64() - c0;
             if (head + nr > ring_rows) head = 0;  // same rule as the loader: a record's rows never wrap
             return head;
         };
-        auto release_rows = [&](int nr) {
-            // ring rows written with generic stores (local tasks) are overwritten by TMA once released
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        auto release_rows = [&](int nr, bool written = false) {
+            // ring rows written with generic stores (local tasks only) are overwritten by TMA once released
+#ifdef CHB_AB_RELEASE_FENCE_ALL
+            written = true;
+#endif
+#ifdef CHB_AB_NO_RELEASE_FENCE
+            written = false;
+#endif
+            if (written) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.rempty + j % kRowBars);
             j += 1;
@@ -772,7 +784,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
                             for (int e = 0; e < n_out; ++e) __stcg(out + (size_t) e * kp, ring_at(lbase, n_int + e));
                         }
                     }
-                    release_rows(lrows);
+                    release_rows(lrows, true);
                 } else if (type == REC_BEGIN_ZERO) {
                     row0 = (int) h.y;
                     w = (int) h.z;
@@ -807,7 +819,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
         // publish: every compute warp's stores of this task are done before the flag is released
         if (n_compute > 1) named_barrier(1, n_compute * 32); else __syncwarp();
         if (leader) {
-            if (a.trace) {
+            if (TRACE) {
                 a.trace[8 * (size_t) task + 2] = global_ns();
                 a.trace[8 * (size_t) task + 3] = (unsigned long long) wait_cycles;
             }
@@ -817,7 +829,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
     }
 }
 
-template <typename F, bool UPPER, bool EXACT>
+template <typename F, bool UPPER, bool EXACT, bool TRACE>
 __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -847,16 +859,19 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
     }
     __syncthreads();
     if (warp == n_compute) loader_warp<F, UPPER>(a, sm, lane);
-    else compute_warp<F, UPPER, EXACT>(a, sm, warp, lane, n_compute);
+    else compute_warp<F, UPPER, EXACT, TRACE>(a, sm, warp, lane, n_compute);
 }
 
 }  // namespace sweep
 
 // _exact: kernels for CHB_EXACT_ORDER schedules (packed triangles, IEEE division); the fast kernels do not
-// carry that code (instruction footprint).
+// carry that code (instruction footprint).  _trace: the CHB_TRACE=1 variants with the per-task timestamps.
 #define CHB_SWEEP(NAME, T, UP, EX)                                                             \
     extern "C" __global__ void __launch_bounds__(160, 2) NAME(const chb::SweepArgs<T> a) {       \
-        sweep::sweep_worker<T, UP, EX>(a);                                                     \
+        sweep::sweep_worker<T, UP, EX, false>(a);                                              \
+    }                                                                                          \
+    extern "C" __global__ void __launch_bounds__(160, 2) NAME##_trace(const chb::SweepArgs<T> a) { \
+        sweep::sweep_worker<T, UP, EX, true>(a);                                               \
     }
 
 CHB_SWEEP(chb_sweep_f32_lower, float, false, false)
