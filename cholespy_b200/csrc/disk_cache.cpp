@@ -14,7 +14,7 @@ namespace chb {
 namespace {
 
 constexpr uint32_t kMagic = 0x31424843u;  // "CHB1"
-constexpr uint32_t kFormat = 3;           // bump whenever a serialised struct or a record layout changes
+constexpr uint32_t kFormat = 4;           // bump whenever a serialised struct or a record layout changes
 
 // 64-bit multiply-xorshift mixer over 8-byte words (two differently seeded lanes make the 128-bit key)
 struct Hasher {

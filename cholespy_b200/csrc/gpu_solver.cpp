@@ -91,7 +91,8 @@ int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 R
 // (four CTAs per SM at 128 single-precision right-hand sides; measured: occupancy beats ring depth).
 int sweep_ring_rows(int elem, int k, int local_rows) {
     const int row_bytes = padded_rhs(k) * elem;
-    int budget_kb = 36;
+    // f32: six CTAs per SM at 128 columns (sweep.cuh: CHB_SWEEP_MIN_CTAS_F32) leave 20 KB next to the four slab pages
+    int budget_kb = elem == 4 ? 20 : 36;
     if (const char *v = std::getenv("CHB_RING_KB")) budget_kb = std::max(1, std::atoi(v));
     int slack = 16;  // rows beyond the largest local task: one full block next to it (measured on cfg4: 16 beats 32, one more CTA per SM)
     if (const char *v = std::getenv("CHB_RING_SLACK")) slack = std::max(16, std::atoi(v));
@@ -142,6 +143,13 @@ size_t front_smem_bytes(int elem, int k, int page_bytes, int ring_rows) {
 
 }  // namespace
 
+// Flag bits of SweepTask::bytes in the replicated (ticket-ordered) task table of a panel image; the tables the
+// kernels walk (split_tasks) carry plain byte counts (+ the ticket-batch hint in bits 28-30 for the persistent kernel).
+constexpr uint32_t kTaskBytesMask = 0x03ffffffu;    // bits 0-25: bytes of the task's record stream
+constexpr uint32_t kTaskLocalKept = 1u << 26;       // a local task left to the persistent kernel (too large for the local-task kernel)
+constexpr uint32_t kTaskLevelParity = 1u << 27;     // parity of the task's dependency level (level boundaries in ticket order)
+constexpr uint32_t kTaskLocalKernel = 1u << 31;     // a local task the local-task kernel executes
+
 void ImageShape::to_words(int64_t *w) const {
     w[0] = n, w[1] = nnz;
     for (int u = 0; u < 2; ++u) {
@@ -153,7 +161,7 @@ void ImageShape::to_words(int64_t *w) const {
     w[15] = n_contrib_rows;
     w[16] = front;
     for (int u = 0; u < 2; ++u) w[17 + u] = n_w_rows[u], w[19 + u] = max_stage_rows[u];
-    w[21] = n_warps, w[22] = page_bytes, w[23] = local_rows_cap[0] | local_rows_cap[1] << 16;
+    w[21] = n_warps, w[22] = page_bytes, w[23] = local_rows_cap[0] | local_rows_cap[1] << 16 | main_local_rows[0] << 32 | main_local_rows[1] << 48;
 }
 ImageShape ImageShape::from_words(const int64_t *w) {
     ImageShape s;
@@ -169,6 +177,7 @@ ImageShape ImageShape::from_words(const int64_t *w) {
     for (int u = 0; u < 2; ++u) s.n_w_rows[u] = w[17 + u], s.max_stage_rows[u] = w[19 + u];
     s.n_warps = w[21], s.page_bytes = w[22];
     s.local_rows_cap[0] = w[23] & 0xffff, s.local_rows_cap[1] = w[23] >> 16 & 0xffff;
+    s.main_local_rows[0] = w[23] >> 32 & 0xffff, s.main_local_rows[1] = w[23] >> 48 & 0x7fff;
     return s;
 }
 
@@ -212,17 +221,18 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
     // 8 while at least kWideLevel tasks of the same dependency level are still to be handed out, else 1
     size_t kWideLevel = 16384;
     if (const char *v = std::getenv("CHB_WIDE_LEVEL")) kWideLevel = (size_t) std::max(1, std::atoi(v));
-    // selection rule of the local-task kernel: CHB_LOCAL_KERNEL=0 leaves every task to the persistent kernel (the
-    // round-1 behaviour); CHB_LOCAL_KERNEL_ROWS="fwd,bwd" / CHB_LOCAL_KERNEL_BYTES: the per-warp budget
+    // selection rule of the local-task kernel: every local task by default; CHB_LOCAL_KERNEL=0 leaves them all to the
+    // persistent kernel (the round-1 behaviour); CHB_LOCAL_KERNEL_ROWS="fwd,bwd" / CHB_LOCAL_KERNEL_BYTES leave
+    // the ones holding more rows / records than that to it (tuning)
     const bool upper = &d == &m_sweep[1];
     bool use_local = true;
-    int rows_cap = upper ? 44 : 28, bytes_cap = 3584;
+    int rows_cap = 255, bytes_cap = 32768, rows_max = 0;
     if (const char *v = std::getenv("CHB_LOCAL_KERNEL")) use_local = std::atoi(v) != 0;
     if (const char *v = std::getenv("CHB_LOCAL_KERNEL_ROWS")) {
         int f = 0, b = 0;
         if (std::sscanf(v, "%d%*[,:]%d", &f, &b) == 2) rows_cap = std::max(1, std::min(255, upper ? b : f));
     }
-    if (const char *v = std::getenv("CHB_LOCAL_KERNEL_BYTES")) bytes_cap = std::max(256, std::atoi(v));
+    if (const char *v = std::getenv("CHB_LOCAL_KERNEL_BYTES")) bytes_cap = std::max(256, std::min(32768, std::atoi(v)));
     const size_t nt = img.order.size();
     size_t level_end = 0;
     for (size_t t = 0; t < nt; ++t) {
@@ -231,7 +241,7 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
             level_end = t + 1;
             while (level_end < nt && img.tasks[(size_t) img.order[level_end]].level == src.level) ++level_end;
         }
-        if (src.bytes >= (1u << 28)) throw std::logic_error("sweep image: task slab too large");
+        if (src.bytes > kTaskBytesMask) throw std::logic_error("sweep image: task slab too large");
         by_ticket[t] = src;
         by_ticket[t].level = (uint32_t) img.order[t];
         by_ticket[t].bytes |= (level_end - t >= kWideLevel ? 7u : 0u) << 28;
@@ -242,19 +252,30 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
         if (use_local && (head[0] & 0x3fu) == (uint32_t) REC_LOCAL_LOAD) {
             const int n_int = (int) (head[2] & 0xffffu), n_ext = (int) (head[2] >> 16);
             const int rows = upper ? n_int + n_ext : n_int;   // forward contributions go straight to global memory
-            if (rows <= rows_cap && (int) src.bytes <= bytes_cap) by_ticket[t].bytes |= 1u << 31;
+            if (rows <= rows_cap && (int) src.bytes <= bytes_cap) by_ticket[t].bytes |= kTaskLocalKernel, rows_max = std::max(rows_max, rows);
+            else by_ticket[t].bytes |= kTaskLocalKept, d.main_local_rows = std::max(d.main_local_rows, n_int + n_ext);
+        } else if ((head[0] & 0x3fu) == (uint32_t) REC_LOCAL_LOAD) {
+            by_ticket[t].bytes |= kTaskLocalKept;
+            d.main_local_rows = std::max(d.main_local_rows, (int) (head[2] & 0xffffu) + (int) (head[2] >> 16));
         }
+        if (src.level & 1u) by_ticket[t].bytes |= kTaskLevelParity;
     }
-    d.local_rows_cap = rows_cap;
+    d.local_rows_cap = rows_max;
     h2d(d.slab, img.slab.data(), img.slab.size());
     h2d(d.tasks, by_ticket.data(), sizeof(TaskDesc) * by_ticket.size());
     sync0();
     split_tasks(d, by_ticket.data());
 }
 
-// The persistent kernel's and the local-task kernel's task tables, derived from the replicated one (replicas
-// receive `tasks` from a peer and derive theirs on first use).
+// The task tables of the three executors of a panel sweep, derived from the replicated one (replicas receive
+// `tasks` from a peer and derive theirs on first use):
+//   local  -- local tasks taken by the local-task kernel (bit 31),
+//   wide   -- the panel tasks of the wide dependency levels next to the leaves, level by level (plain launches),
+//   main   -- everything else: the persistent kernel.
+// Wide levels (opt-in, CHB_WIDE_MIN_TASKS=N > 0): forward, every level up to the last one holding >= N such tasks;
+// backward, every level from the first such one on.  Exact-order images, or N = 0 (the default): none.
 void GpuSolver::split_tasks(SweepDev &s, const void *host_tasks) {
+    const bool upper = &s == &m_sweep[1];
     std::vector<TaskDesc> all((size_t) s.n_tasks);
     if (host_tasks) {
         std::memcpy(all.data(), host_tasks, sizeof(TaskDesc) * all.size());
@@ -262,23 +283,70 @@ void GpuSolver::split_tasks(SweepDev &s, const void *host_tasks) {
         d2h(all.data(), s.tasks, sizeof(TaskDesc) * all.size());
         sync0();
     }
-    std::vector<TaskDesc> main_t, local_t;
-    uint32_t cap = 0;
-    for (const TaskDesc &t : all) {
-        if (t.bytes >> 31) {
-            local_t.push_back(t);
-            cap = std::max(cap, t.bytes & 0x0fffffffu);
+    // dependency level of every task (ticket order is level order; bit 27 = the level's parity) and the number of
+    // wide-kernel candidates per level
+    std::vector<int> level_of(all.size(), 0);
+    std::vector<int> candidates;
+    int level = 0;
+    for (size_t t = 0; t < all.size(); ++t) {
+        if (t > 0 && ((all[t].bytes ^ all[t - 1].bytes) & kTaskLevelParity)) level += 1;
+        level_of[t] = level;
+        if ((size_t) level >= candidates.size()) candidates.resize((size_t) level + 1, 0);
+        if (!(all[t].bytes & (kTaskLocalKernel | kTaskLocalKept))) candidates[(size_t) level] += 1;
+    }
+    int min_tasks = 0;  // measured (profiles/r02x_wide_ab2.log): no gain over the persistent kernel on cfg4 / cfg5 at any threshold; opt-in
+    if (const char *v = std::getenv("CHB_WIDE_MIN_TASKS")) min_tasks = std::atoi(v);
+    int wide_lo = 0, wide_hi = -1;  // levels [wide_lo, wide_hi] go to the wide kernel
+    if (min_tasks > 0 && !m_exact && !all.empty()) {
+        const int n_levels = (int) candidates.size();
+        if (!upper) {
+            for (int l = 0; l < n_levels; ++l)
+                if (candidates[(size_t) l] >= min_tasks) wide_hi = l;
+            // a wide level must not read what a local task left to the persistent kernel (which runs last) produces
+            for (size_t t = 0; t < all.size(); ++t)
+                if (all[t].bytes & kTaskLocalKept) wide_hi = std::min(wide_hi, level_of[t] - 1);
         } else {
-            main_t.push_back(t);
+            for (int l = n_levels - 1; l >= 0; --l)
+                if (candidates[(size_t) l] >= min_tasks) wide_lo = l, wide_hi = n_levels - 1;
+            // a local task left to the persistent kernel (which runs first) must not wait for a wide level
+            for (size_t t = 0; t < all.size(); ++t)
+                if (all[t].bytes & kTaskLocalKept) wide_lo = std::max(wide_lo, level_of[t] + 1);
+        }
+    }
+    std::vector<TaskDesc> main_t, local_t, wide_t;
+    s.wide_levels.clear();
+    uint32_t cap = 0;
+    int cur_level = -1;
+    for (size_t t = 0; t < all.size(); ++t) {
+        TaskDesc d = all[t];
+        const uint32_t flags = d.bytes;
+        d.bytes &= ~(kTaskLocalKernel | kTaskLocalKept | kTaskLevelParity);
+        if (flags & kTaskLocalKernel) {
+            d.bytes &= kTaskBytesMask;
+            local_t.push_back(d);
+            cap = std::max(cap, d.bytes);
+        } else if (!(flags & kTaskLocalKept) && level_of[t] >= wide_lo && level_of[t] <= wide_hi) {
+            d.bytes &= kTaskBytesMask;
+            if (level_of[t] != cur_level) {
+                cur_level = level_of[t];
+                s.wide_levels.push_back({(int) wide_t.size(), 0});
+            }
+            s.wide_levels.back().second += 1;
+            wide_t.push_back(d);
+        } else {
+            main_t.push_back(d);  // keeps the ticket-batch hint (bits 28-30)
         }
     }
     s.n_main = (int) main_t.size();
     s.n_local = (int) local_t.size();
+    s.n_wide = (int) wide_t.size();
     s.local_slab_cap = (int) ((cap + 15u) & ~15u);
     s.main_tasks = dev_alloc(sizeof(TaskDesc) * std::max<size_t>(main_t.size(), 1));
     s.local_tasks = dev_alloc(sizeof(TaskDesc) * std::max<size_t>(local_t.size(), 1));
+    s.wide_tasks = dev_alloc(sizeof(TaskDesc) * std::max<size_t>(wide_t.size(), 1));
     if (!main_t.empty()) h2d(s.main_tasks, main_t.data(), sizeof(TaskDesc) * main_t.size());
     if (!local_t.empty()) h2d(s.local_tasks, local_t.data(), sizeof(TaskDesc) * local_t.size());
+    if (!wide_t.empty()) h2d(s.wide_tasks, wide_t.data(), sizeof(TaskDesc) * wide_t.size());
     sync0();
     s.split = true;
 }
@@ -502,6 +570,7 @@ GpuSolver::GpuSolver(int device, int elem_size, const ImageShape &shape)
         m_sweep[u].n_task_levels = (int) shape.n_task_levels[u];
         m_sweep[u].max_local_rows = (int) shape.max_local_rows[u];
         m_sweep[u].local_rows_cap = (int) shape.local_rows_cap[u];
+        m_sweep[u].main_local_rows = (int) shape.main_local_rows[u];
         m_sweep[u].n_w_rows = shape.n_w_rows[u];
         m_sweep[u].max_stage_rows = (int) shape.max_stage_rows[u];
         m_sweep[u].page_bytes = (int) shape.page_bytes;
@@ -527,6 +596,7 @@ GpuSolver::~GpuSolver() {
         dev_free(s.trace);
         dev_free(s.main_tasks);
         dev_free(s.local_tasks);
+        dev_free(s.wide_tasks);
     }
     dev_free(m_counters);
     dev_free(m_tmp);
@@ -556,6 +626,7 @@ ImageShape GpuSolver::shape() const {
         s.n_task_levels[u] = m_sweep[u].n_task_levels;
         s.max_local_rows[u] = m_sweep[u].max_local_rows;
         s.local_rows_cap[u] = m_sweep[u].local_rows_cap;
+        s.main_local_rows[u] = m_sweep[u].main_local_rows;
     }
     s.exact_order = m_exact ? 1 : 0;
     s.n_contrib_rows = m_sweep[0].n_contrib_rows;
@@ -586,15 +657,13 @@ static int local_cpl(int elem, int k) {
     return cpl;
 }
 
-// The local tasks of one sweep as a plain launch (local_sweep.cuh).  False (nothing launched) when there are none
-// or when the largest one does not fit an SM's shared memory: the caller then leaves them to the persistent kernel.
-bool GpuSolver::local_sweep(bool upper, int k, const void *src, void *dst, int ld, bool probe_only) {
+// The local tasks of one sweep as a plain launch (local_sweep.cuh).  The selection rule (upload_sweep) bounds the
+// shared memory a warp needs: 255 rows x 512 B + 2 x 32 KB of records at most.
+void GpuSolver::local_sweep(bool upper, int k, const void *src, void *dst, int ld) {
     const SweepDev &s = m_sweep[upper ? 1 : 0];
-    if (s.n_local == 0) return false;
+    if (s.n_local == 0) return;
     const int cpl = local_cpl(m_elem, k);
     const size_t smem = 2 * (size_t) s.local_slab_cap + (size_t) s.local_rows_cap * 32 * (size_t) cpl * (size_t) m_elem;
-    if (smem > (size_t) 200 * 1024) return false;
-    if (probe_only) return true;
     char name[64];
     snprintf(name, sizeof name, "chb_local_%s_c%d_%s%s", m_elem == 4 ? "f32" : "f64", cpl, upper ? "upper" : "lower", m_exact ? "_exact" : "");
     CUfunction fn = kernel(m_dev, name);
@@ -637,21 +706,82 @@ bool GpuSolver::local_sweep(bool upper, int k, const void *src, void *dst, int l
     if (const char *cap = std::getenv("CHB_LOCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(cap)));
     const int grid = (int) std::max<long long>(1, std::min<long long>(items, (long long) per_sm * m_dev->sm_count));
     cuda_check(cuLaunchKernel(fn, (unsigned) grid, 1, 1, 32, 1, 1, (unsigned) smem, nullptr, params, nullptr));
-    return true;
+}
+
+// The wide dependency levels of one sweep, one plain launch per level (wide_sweep.cuh), in sweep order.
+void GpuSolver::wide_sweep(bool upper, int k, const void *src, void *dst, int ld) {
+    const SweepDev &s = m_sweep[upper ? 1 : 0];
+    if (s.wide_levels.empty()) return;
+    char name[64];
+    snprintf(name, sizeof name, "chb_wide_%s_%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower");
+    CUfunction fn = kernel(m_dev, name);
+    if (!fn) throw std::runtime_error(driver_error_text());
+    const size_t smem = 2 * (size_t) page_bytes_for(m_elem);
+    const int block = 32 * sweep_warps(k);
+    cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
+    int per_sm = max_resident_blocks(m_dev, fn, block, smem) / std::max(1, m_dev->sm_count);
+    if (const char *cap = std::getenv("CHB_WIDE_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(cap)));
+    for (const std::pair<int, int> &range : s.wide_levels) {
+        auto fill = [&](auto &a) {
+            using A = std::remove_reference_t<decltype(a)>;
+            using Float = std::remove_pointer_t<decltype(A::tmp)>;
+            a.n_tasks = range.second;
+            a.k = k;
+            a.epoch = m_epoch;
+            a.src_vec = a.dst_vec = 0;
+            a.src_ld = ld;
+            a.dst_ld = ld;
+            a.slab = (const unsigned char *) s.slab;
+            a.tasks = (const SweepTask *) s.wide_tasks + range.first;
+            a.done = (int *) s.done;
+            a.tmp = (Float *) m_tmp;
+            a.src = (const Float *) src;
+            a.dst = (Float *) dst;
+            a.scratch = (Float *) m_scratch;
+            a.rbuf = (Float *) m_rbuf;
+            a.cbuf = (Float *) m_cbuf;
+        };
+        WideArgs<float> a32;
+        WideArgs<double> a64;
+        void *params[1];
+        if (m_elem == 4) {
+            fill(a32);
+            params[0] = &a32;
+        } else {
+            fill(a64);
+            params[0] = &a64;
+        }
+        const int grid = std::max(1, std::min(range.second, per_sm * m_dev->sm_count));
+        cuda_check(cuLaunchKernel(fn, (unsigned) grid, 1, 1, (unsigned) block, 1, 1, (unsigned) smem, nullptr, params, nullptr));
+    }
 }
 
 void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
     if (!m_sweep[upper ? 1 : 0].split) split_tasks(m_sweep[upper ? 1 : 0], nullptr);  // a replica's first solve
-    // local tasks: before the dependency-driven part in the forward sweep (they depend on nothing), after it in the
-    // backward sweep (nothing depends on them)
-    const bool local = local_sweep(upper, k, src, dst, ld, /*probe_only=*/true);
-    if (local && !upper) local_sweep(false, k, src, dst, ld);
+    // Forward: local tasks (they depend on nothing), the wide levels next to the leaves, then the dependency-driven
+    // rest in the persistent kernel.  Backward: the mirror image (nothing depends on the local tasks).
+    if (!upper) {
+        local_sweep(false, k, src, dst, ld);
+        wide_sweep(false, k, src, dst, ld);
+    }
+    persistent_sweep(upper, k, src, dst, ld);
+    if (upper) {
+        wide_sweep(true, k, src, dst, ld);
+        local_sweep(true, k, src, dst, ld);
+    }
+}
+
+void GpuSolver::persistent_sweep(bool upper, int k, const void *src, void *dst, int ld) {
+    const bool local = true;  // the persistent kernel walks its own table (split_tasks)
+    if (m_sweep[upper ? 1 : 0].n_main == 0) return;
     char name[64];
     snprintf(name, sizeof name, "chb_sweep_%s_%s%s%s", m_elem == 4 ? "f32" : "f64", upper ? "upper" : "lower", m_exact ? "_exact" : "",
              m_sweep[upper ? 1 : 0].trace ? "_trace" : "");
     CUfunction fn = kernel(m_dev, name);
     if (!fn) throw std::runtime_error(driver_error_text());
-    const int local_rows = std::max(m_sweep[0].max_local_rows, m_sweep[1].max_local_rows);
+    // the row ring holds the largest local task this kernel still executes (none, usually, with the local-task kernel)
+    const int local_rows = local ? std::max(m_sweep[0].main_local_rows, m_sweep[1].main_local_rows)
+                                 : std::max(m_sweep[0].max_local_rows, m_sweep[1].max_local_rows);
     const size_t smem = sweep_smem_bytes(m_elem, k, local_rows);
     const int block = 32 * (sweep_warps(k) + 1);
     cuda_check(cuFuncSetAttribute(fn, kFuncAttrMaxDynamicSharedSize, (int) smem));
@@ -700,7 +830,6 @@ void GpuSolver::sweep(bool upper, int k, const void *src, void *dst, int ld) {
     if (const char *cap = std::getenv("CHB_SWEEP_CTAS_PER_SM")) grid = std::max(1, std::min(grid, std::atoi(cap) * m_dev->sm_count));
     m_last_grid = grid;
     cuda_check(cuLaunchCooperativeKernel(fn, grid, 1, 1, block, 1, 1, (unsigned) smem, nullptr, params));
-    if (local && upper) local_sweep(true, k, src, dst, ld);
 }
 
 void GpuSolver::front_sweep(bool upper, int k, const void *src, void *dst, int ld) {

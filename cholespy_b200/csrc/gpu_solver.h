@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "cuda_driver.h"
@@ -27,10 +28,12 @@ struct SweepDev {
     void *slab = nullptr;    // record stream
     void *tasks = nullptr;   // SweepTask[n_tasks], in ticket order (bit 31 of `bytes`: a local task)
     // derived from `tasks` (split_tasks): what the persistent kernel and the local-task kernel walk
-    void *main_tasks = nullptr, *local_tasks = nullptr;
-    int n_main = 0, n_local = 0;
+    void *main_tasks = nullptr, *local_tasks = nullptr, *wide_tasks = nullptr;
+    int n_main = 0, n_local = 0, n_wide = 0;
+    std::vector<std::pair<int, int>> wide_levels;  // (first, count) into wide_tasks per wide dependency level, in sweep order
     int local_slab_cap = 0;  // largest record stream among the local-kernel tasks, bytes
     int local_rows_cap = 0;  // most rows a local-kernel task holds in shared memory (forward: its unknowns; backward: + external rows)
+    int main_local_rows = 0; // largest local task left to the persistent kernel (sizes its row ring), rows
     bool split = false;
     void *done = nullptr;    // int32[n_tasks]: epoch flags (scratch, not part of the image)
     void *trace = nullptr;   // uint64[8 * n_tasks] when CHB_TRACE=1 (debug timeline), else null
@@ -66,6 +69,7 @@ struct ImageShape {
     int64_t n_w_rows[2] = {0, 0}, max_stage_rows[2] = {0, 0};
     int64_t n_warps = 0, page_bytes = 0;
     int64_t local_rows_cap[2] = {0, 0};  // selection rule of the local-task kernel (rows a task may hold), per sweep
+    int64_t main_local_rows[2] = {0, 0}; // largest local task left to the persistent kernel, per sweep
     static constexpr int kWords = 24;
     void to_words(int64_t *w) const;
     static ImageShape from_words(const int64_t *w);
@@ -105,7 +109,11 @@ public:
     const TriangleAnalysis &triangle(bool lower) const { return lower ? m_lower : m_upper; }
     const std::vector<int> &perm_host() const { return m_perm_host; }
     int last_grid() const { return m_last_grid; }
-    int launches_per_solve() const { return 2 + (m_sweep[0].n_local > 0 ? 1 : 0) + (m_sweep[1].n_local > 0 ? 1 : 0); }
+    int launches_per_solve() const {
+        int n = 0;
+        for (const SweepDev &s : m_sweep) n += (s.n_main > 0 || !s.split ? 1 : 0) + (s.n_local > 0 ? 1 : 0) + (int) s.wide_levels.size();
+        return n;
+    }
     bool front() const { return m_front; }
     // Blocks until the legacy stream is idle and returns the sweep watchdog's error word (0: fine; non-zero: a
     // dependency never arrived -- a schedule or kernel bug; the results of the last solves are invalid).
@@ -125,7 +133,9 @@ private:
     void upload_sweep(SweepDev &d, const SweepImage &img);
     void sweep(bool upper, int k, const void *src, void *dst, int ld);
     void split_tasks(SweepDev &s, const void *host_tasks);
-    bool local_sweep(bool upper, int k, const void *src, void *dst, int ld, bool probe_only = false);
+    void persistent_sweep(bool upper, int k, const void *src, void *dst, int ld);
+    void local_sweep(bool upper, int k, const void *src, void *dst, int ld);
+    void wide_sweep(bool upper, int k, const void *src, void *dst, int ld);
     void front_sweep(bool upper, int k, const void *src, void *dst, int ld);
     void upload_front(SweepDev &d, const FrontImage &img);
 

@@ -77,6 +77,25 @@ struct LocalArgs {
     Float *cbuf;          // forward contributions of the local tasks
 };
 
+// One wide dependency level of a panel sweep as a plain launch (wide_sweep.cuh: chb_wide_*).
+template <typename Float>
+struct WideArgs {
+    int n_tasks;          // the level's tasks
+    int k;
+    int epoch;
+    int src_vec, dst_vec; // a lane's columns of a row of b / x can be moved as one vector (alignment of base and stride)
+    int src_ld, dst_ld;   // elements between consecutive rows of b / x
+    const unsigned char *slab;
+    const SweepTask *tasks;     // the level's tasks; `level` = task id = index of its ready flag
+    int *done;            // per-task epoch flags (published for the launches that follow)
+    Float *tmp;           // (n, round4(k)) work vector in permuted order
+    const Float *src;     // forward: user's b
+    Float *dst;           // backward: user's x
+    Float *scratch;       // partial tiles of chunk tasks
+    Float *rbuf;          // residual vector of the inverse super-blocks
+    Float *cbuf;          // forward contributions of the local tasks
+};
+
 // One front sweep (front_sweep.cuh: chb_front_*).  See front_schedule.h for the record format.
 template <typename Float>
 struct FrontArgs {

@@ -106,4 +106,5 @@ extern "C" __global__ void __launch_bounds__(256) chb_etree_round(const chb::Etr
 
 #include "sweep.cuh"
 #include "local_sweep.cuh"
+#include "wide_sweep.cuh"
 #include "front_sweep.cuh"

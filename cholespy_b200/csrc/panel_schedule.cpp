@@ -675,7 +675,9 @@ struct Builder {
             sub_count[q] += sub_count[P];
             first[q] = std::min(first[q], first[P]);
         }
-        const int max_rows = opt.local_rows > 0 ? opt.local_rows : (img.elem == 8 ? 32 : 36);
+        // measured with the local-task kernel (cfg4 / cfg5 at 128 RHS, profiles/r02x_local_sched*.log): 24 rows; up to
+        // 36 / 24 is as good in f32, larger tasks cost that kernel its occupancy
+        const int max_rows = opt.local_rows > 0 ? opt.local_rows : 24;
         const int max_ext = opt.local_ext > 0 ? opt.local_ext : (img.elem == 8 ? 31 : 24);  // <= 31: one loader lane per external row
         std::vector<int> root_of(np, -1);  // root of the local task a panel belongs to, or -1
         for (int P = np - 1; P >= 0; --P) {

@@ -94,7 +94,7 @@ enum RecordType : uint32_t {
 };
 
 struct ScheduleOptions {
-    int local_rows = 0;       // a complete subtree becomes one LOCAL task up to this many rows (0: 36 f32 / 32 f64)
+    int local_rows = 0;       // a complete subtree becomes one LOCAL task up to this many rows (0: 24)
     int local_ext = 0;        // ... this many external rows below its root panel (backward sweep; 0: 24 f32 / 31 f64)
     int local_cost = 65536;   // ... and this many stored values
     int split_cost = 4096;    // a panel with more values than this is split into chunk tasks

@@ -866,19 +866,28 @@ __device__ __forceinline__ void sweep_worker(const SweepArgs<F> &a) {
 
 // _exact: kernels for CHB_EXACT_ORDER schedules (packed triangles, IEEE division); the fast kernels do not
 // carry that code (instruction footprint).  _trace: the CHB_TRACE=1 variants with the per-task timestamps.
-#define CHB_SWEEP(NAME, T, UP, EX)                                                             \
-    extern "C" __global__ void __launch_bounds__(160, 2) NAME(const chb::SweepArgs<T> a) {       \
-        sweep::sweep_worker<T, UP, EX, false>(a);                                              \
-    }                                                                                          \
-    extern "C" __global__ void __launch_bounds__(160, 2) NAME##_trace(const chb::SweepArgs<T> a) { \
-        sweep::sweep_worker<T, UP, EX, true>(a);                                               \
+// CTAs per SM the fast kernels are compiled for (register cap): measured on cfg4 with the local tasks gone to their own
+// kernel (profiles/r02x_ctas_ab.log) 4 -> 5 -> 6 CTAs per SM = 10.48 -> 9.50 -> 9.43 ms; 64 registers is the last
+// spill-free point in f32 (7 CTAs: 24 B of stack); f64: 4 CTAs (96 registers, cfg5 6.19 -> 5.68 ms), 5 spill (6.8 ms).
+#ifndef CHB_SWEEP_MIN_CTAS_F32
+#define CHB_SWEEP_MIN_CTAS_F32 6
+#endif
+#ifndef CHB_SWEEP_MIN_CTAS_F64
+#define CHB_SWEEP_MIN_CTAS_F64 4
+#endif
+#define CHB_SWEEP(NAME, T, UP, EX, MINB)                                                           \
+    extern "C" __global__ void __launch_bounds__(160, MINB) NAME(const chb::SweepArgs<T> a) {       \
+        sweep::sweep_worker<T, UP, EX, false>(a);                                                  \
+    }                                                                                              \
+    extern "C" __global__ void __launch_bounds__(160, MINB) NAME##_trace(const chb::SweepArgs<T> a) { \
+        sweep::sweep_worker<T, UP, EX, true>(a);                                                   \
     }
 
-CHB_SWEEP(chb_sweep_f32_lower, float, false, false)
-CHB_SWEEP(chb_sweep_f32_upper, float, true, false)
-CHB_SWEEP(chb_sweep_f64_lower, double, false, false)
-CHB_SWEEP(chb_sweep_f64_upper, double, true, false)
-CHB_SWEEP(chb_sweep_f32_lower_exact, float, false, true)
-CHB_SWEEP(chb_sweep_f32_upper_exact, float, true, true)
-CHB_SWEEP(chb_sweep_f64_lower_exact, double, false, true)
-CHB_SWEEP(chb_sweep_f64_upper_exact, double, true, true)
+CHB_SWEEP(chb_sweep_f32_lower, float, false, false, CHB_SWEEP_MIN_CTAS_F32)
+CHB_SWEEP(chb_sweep_f32_upper, float, true, false, CHB_SWEEP_MIN_CTAS_F32)
+CHB_SWEEP(chb_sweep_f64_lower, double, false, false, CHB_SWEEP_MIN_CTAS_F64)
+CHB_SWEEP(chb_sweep_f64_upper, double, true, false, CHB_SWEEP_MIN_CTAS_F64)
+CHB_SWEEP(chb_sweep_f32_lower_exact, float, false, true, 2)
+CHB_SWEEP(chb_sweep_f32_upper_exact, float, true, true, 2)
+CHB_SWEEP(chb_sweep_f64_lower_exact, double, false, true, 2)
+CHB_SWEEP(chb_sweep_f64_upper_exact, double, true, true, 2)

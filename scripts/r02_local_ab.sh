@@ -1,8 +1,15 @@
-# A/B of the local-task kernel (run under gpurun)
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02x_pytest.log 2>&1; tail -3 gpurun_out/r02x_pytest.log
-B="CHB_LOCAL_KERNEL=1,CHB_LOCAL_KERNEL_ROWS=20:36,CHB_LOCAL_KERNEL_ROWS=24:40,CHB_LOCAL_KERNEL_ROWS=36:60+CHB_LOCAL_KERNEL_BYTES=9000,CHB_LOCAL_KERNEL=0"
-timeout 900 python scripts/sweep_experiments.py ico8 f 128,3 0 "" "$B" 2>&1 | grep -E "^k=|rror|^=="
-timeout 900 python scripts/sweep_experiments.py cfg5 d 128 0 "" "$B" 2>&1 | grep -E "^k=|rror|^=="
-timeout 900 python scripts/sweep_experiments.py ico9 f 128 0 "" "CHB_LOCAL_KERNEL=1,CHB_LOCAL_KERNEL=0" 2>&1 | grep -E "^k=|rror|^=="
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:chb_ --csv --log-file gpurun_out/r02w_launches_ico8.csv python scripts/solve_once.py ico8 f 128 3 > /dev/null 2>&1
-grep -E "chb_(local|sweep)" gpurun_out/r02w_launches_ico8.csv | cut -d, -f5,9,15 | tail -4
+# occupancy variants of the persistent kernel (run under gpurun)
+run() { # variant, ring kb, workload, dtype, k
+  if [ "$1" = main ]; then unset CHB_LIB_VARIANT; else export CHB_LIB_VARIANT=$1; fi
+  echo "=== variant $1 ring $2 KB: $3 $4"
+  CHB_RING_KB=$2 timeout 900 python scripts/sweep_experiments.py $3 $4 "$5" 2>&1 | grep -E "^k=|rror"
+}
+run main 36 cfg5 d 128,3
+run d4 36 cfg5 d 128,3
+run d5 27 cfg5 d 128,3
+run d5 20 cfg5 d 128,3
+unset CHB_LIB_VARIANT
+echo "=== defaults"
+timeout 900 python scripts/sweep_experiments.py ico8 f 128,64,32,3,1 2>&1 | grep -E "^k=|rror"
+timeout 900 python scripts/sweep_experiments.py ico9 f 128 2>&1 | grep -E "^k=|rror"
+timeout 900 python scripts/sweep_experiments.py ico6 f 128 2>&1 | grep -E "^k=|rror"

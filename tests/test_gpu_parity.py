@@ -351,6 +351,36 @@ def test_front_path_vs_oracle(name, warps, dtype, oracle_mod, native_lib, monkey
         assert rel_residual(A, x, b) < (1e-5 if dtype == np.float32 else 1e-13), (name, k)
 
 
+# The three executors of a panel sweep (csrc/gpu_solver.cpp: split_tasks): local-task kernel, wide-level kernel,
+# persistent kernel.  Small problems have no wide level by default; CHB_WIDE_MIN_TASKS=1 sends every level but the
+# narrow top through the wide-level kernel, "persistent" is the round-1 path (one persistent kernel per sweep).
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["wide-all", "wide-some", "local-some", "persistent"])
+@pytest.mark.parametrize("name", ["ico3", "ico5", "grid2d-40", "grid3d-10", "localspd-30"])
+def test_sweep_executors_vs_oracle(name, mode, dtype, oracle_mod, native_lib, monkeypatch):
+    env = {"wide-all": {"CHB_WIDE_MIN_TASKS": "1"}, "wide-some": {"CHB_WIDE_MIN_TASKS": "20"},
+           "local-some": {"CHB_WIDE_MIN_TASKS": "1", "CHB_LOCAL_KERNEL_ROWS": "12:24"},
+           "persistent": {"CHB_WIDE_MIN_TASKS": "0", "CHB_LOCAL_KERNEL": "0"}}[mode]
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    A = problems.to_scipy_csc(p)
+    s = _solver(p, dtype)
+    if mode == "persistent":
+        assert s.info()["launches_per_solve"] == 2
+    elif mode == "wide-all":
+        assert s.info()["launches_per_solve"] > 4
+    rng = np.random.default_rng(47)
+    for k in (1, 3, 4, 33, 64, 126, 128):
+        b = rng.random((p["n"], k)).astype(dtype)
+        x = _gpu_solve(s, b)
+        x_or = oracle_mod.solve(cp, ri, v, perm, b)
+        assert max_rel_err(x, x_or) < TOL[np.dtype(dtype)], (name, mode, k)
+        assert rel_residual(A, x, b) < (1e-5 if dtype == np.float32 else 1e-13), (name, mode, k)
+    s.check_error()
+
+
 def test_analysis_row_kernel_matches_etree_kernel(oracle_mod, native_lib, monkeypatch):
     """The default analysis (elimination-tree heights / depths by pointer doubling, chb_etree_round) and the row-by-row
     restatement of the reference's kernels (chb_analysis, CHB_ANALYSIS=rows) give the same arrays, on meshes and on
