@@ -440,24 +440,27 @@ def run_b200(args, name, p, k_total, dtype):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # dominant kernel = the sweep kernel, launched twice per step (forward, backward); per-launch
-        # algorithmic bytes = Bytes(k)/2, per-launch duration = step/2 (this rank's shard).
+        # one step = the launches of one solve (per sweep: the local-task kernel + the persistent kernel, mirrored in the
+        # backward sweep; info()["launches_per_solve"]); achieved = Bytes(k) of the step / the step's device time (this
+        # rank's shard).  The per-kernel shares are in the committed launch list (profiles/).
         abytes = algorithmic_bytes(n, z, k, s)
         achieved = abytes / (dev_ms * 1e-3) / 1e9
-        # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture of THIS build: the entry names
-        # the kernels and the grid it was taken with and is ignored (traffic = null) if either differs from this run
+        # dram__bytes_read + dram__bytes_write of one step (summed over its launches) from the committed ncu capture of THIS
+        # build: the entry names the kernels and the grid it was taken with and is ignored (traffic = null) if either differs
         traffic, traffic_source = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and world == 1:
             entry = json.load(open(tpath)).get("%s/k%d/%s" % (args.workload, k_total, "f32" if dtype == np.float32 else "f64"))
             kernels = "chb_front" if info.get("front_image") else "chb_sweep"
-            if isinstance(entry, dict) and entry.get("grid") == info.get("grid") and str(entry.get("kernels", "")).startswith(kernels):
-                traffic, traffic_source = entry.get("bytes_per_launch"), entry.get("source")
+            if (isinstance(entry, dict) and entry.get("grid") == info.get("grid") and kernels in str(entry.get("kernels", ""))
+                    and entry.get("launches") == info.get("launches_per_solve")):
+                traffic, traffic_source = entry.get("bytes_per_step"), entry.get("source")
             elif entry is not None:
                 log("profiles/ncu_traffic.json entry does not match this build (grid/kernels): roofline.traffic = null")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src, "algorithmic_bytes_per_step": abytes,
-                    "launches_per_step": 2, "roofline_columns_per_s": k / (abytes / (peak * 1e9))}
+                    "traffic_per": "step", "launches_per_step": info.get("launches_per_solve", 2),
+                    "roofline_columns_per_s": k / (abytes / (peak * 1e9))}
         cpu_baseline = None
         if not args.no_cpu_baseline:
             from oracle import oracle
@@ -512,7 +515,8 @@ def run_b200(args, name, p, k_total, dtype):
                        "l2": "512 MB flush write between timed steps", "grid": info.get("grid")},
             "e2e": {"value": k_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * k * s,
                     "d2h_bytes_per_step": n * k * s, "ms_per_step": e2e_ms},
-            "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": solver.info().get("launches_per_solve", 2) * args.steps, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
             "relative_residual": resid, "host_cores": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)

@@ -3,8 +3,9 @@
     python scripts/summarize_ncu.py gpurun_out/<name>.ncu-rep profiles/<name>_summary.txt [workload-key]
 
 Writes per-kernel duration, DRAM bytes, throughput, occupancy, issue utilisation and the warp-stall
-distribution; with a workload key (e.g. cfg4/k128/f32) also records the mean DRAM traffic per launch
-in profiles/ncu_traffic.json, which bench.py reports as roofline.traffic.
+distribution; with a workload key (e.g. cfg4/k128/f32) -- the report then has to hold exactly the launches of
+ONE solve -- also records their summed DRAM traffic in profiles/ncu_traffic.json, which bench.py reports as
+roofline.traffic.
 """
 import csv
 import json
@@ -52,8 +53,10 @@ def main():
         path = os.path.join(os.path.dirname(os.path.abspath(out)), "ncu_traffic.json")
         table = json.load(open(path)) if os.path.exists(path) else {}
         gi = hdr.index("launch__grid_size")
-        table[key] = {"bytes_per_launch": sum(traffic) / len(traffic), "grid": int(float(data[0][gi])),
-                      "kernels": data[0][name_i].split("(")[0], "source": "profiles/" + os.path.basename(out)}
+        names = [r[name_i].split("(")[0] for r in data]
+        main = [r for r in data if r[name_i].startswith(("chb_sweep", "chb_front"))] or data
+        table[key] = {"bytes_per_step": sum(traffic), "launches": len(traffic), "grid": int(float(main[0][gi])),
+                      "kernels": " ".join(names), "source": "profiles/" + os.path.basename(out)}
         json.dump(table, open(path, "w"), indent=1, sort_keys=True)
 
 
