@@ -219,7 +219,7 @@ void GpuSolver::upload_sweep(SweepDev &d, const SweepImage &img) {
     std::vector<TaskDesc> by_ticket(img.tasks.size());
     // ... and bits 28-30 of `bytes` say how many tickets a loader may draw together at this position (sweep.cuh):
     // 8 while at least kWideLevel tasks of the same dependency level are still to be handed out, else 1
-    size_t kWideLevel = 16384;
+    size_t kWideLevel = 65536;  // (re-measured with 6 CTAs per SM, profiles/r02x_inv_ab.log: batching tickets rarely pays)
     if (const char *v = std::getenv("CHB_WIDE_LEVEL")) kWideLevel = (size_t) std::max(1, std::atoi(v));
     // selection rule of the local-task kernel: every local task by default; CHB_LOCAL_KERNEL=0 leaves them all to the
     // persistent kernel (the round-1 behaviour); CHB_LOCAL_KERNEL_ROWS="fwd,bwd" / CHB_LOCAL_KERNEL_BYTES leave

@@ -69,7 +69,7 @@ ScheduleOptions schedule_options_from_env() {
     o.local_rows = std::max(0, std::min(240, geti("CHB_LOCAL_ROWS", o.local_rows)));
     o.local_ext = std::max(0, std::min(31, geti("CHB_LOCAL_EXT", o.local_ext)));  // one loader lane per external row
     o.local_cost = std::max(1, geti("CHB_LOCAL_COST", o.local_cost));
-    o.inv_panels = std::max(0, std::min(64, geti("CHB_INV_PANELS", o.inv_panels)));
+    o.inv_panels = std::max(0, std::min(512, geti("CHB_INV_PANELS", o.inv_panels)));
     o.contributions = geti("CHB_CONTRIBUTIONS", o.contributions ? 1 : 0) != 0;
     o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));
     o.chunk_cost = std::max(256, geti("CHB_CHUNK_COST", o.chunk_cost));

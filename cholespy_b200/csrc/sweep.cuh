@@ -102,11 +102,27 @@ __device__ __forceinline__ unsigned long long global_ns();
 // is a budget of anything between milliseconds and minutes: a debugger, compute-sanitizer or a pre-empted context
 // must not trip it).  A dependency that never arrives is a schedule or kernel bug: trap rather than hang the GPU.
 constexpr unsigned long long kWatchdogNs = 20ull * 1000ull * 1000ull * 1000ull;
+#ifndef CHB_AB_COMPUTE_BACKOFF
+#define CHB_AB_COMPUTE_BACKOFF 0
+#endif
+// BACKOFF_NS > 0: a failed attempt is followed by a real sleep (compute warps; CHB_AB_COMPUTE_BACKOFF experiments)
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     unsigned spins = 0;
     unsigned long long t0 = 0;
     for (;;) {
         uint32_t ok;
+#ifdef CHB_AB_NO_HINT
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+#else
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -116,7 +132,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
             : "memory");
+#endif
         if (ok) return;
+        if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
 #ifdef CHB_AB_COUNT_WATCHDOG
         if (++spins > (1u << 22)) __trap();
 #else
@@ -634,7 +652,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
     long long wait_cycles = 0;  // tracing only
 
     for (uint32_t q = 0;; ++q) {
-        mbar_wait(sm.tfull + q % kTaskQueue, (q / kTaskQueue) & 1);
+        mbar_wait<CHB_AB_COMPUTE_BACKOFF>(sm.tfull + q % kTaskQueue, (q / kTaskQueue) & 1);
         const QueuedTask cur = sm.queue[q % kTaskQueue];
         if (cur.ticket >= a.n_tasks) break;
         const int task = cur.task;
@@ -650,7 +668,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
         // waits for the loader to have staged the next record's rows; returns their ring position
         auto acquire_rows = [&](int nr) {
             const long long c0 = TRACE ? clock64() : 0;
-            mbar_wait(sm.rfull + j % kRowBars, (j / kRowBars) & 1);
+            mbar_wait<CHB_AB_COMPUTE_BACKOFF>(sm.rfull + j % kRowBars, (j / kRowBars) & 1);
             if (TRACE) wait_cycles += clock64() - c0;
             if (head + nr > ring_rows) head = 0;  // same rule as the loader: a record's rows never wrap
             return head;
@@ -692,7 +710,7 @@ __device__ __forceinline__ void compute_warp(const SweepArgs<F> &a, const Smem<F
 
         for (uint32_t pg = 0; pg < n_pages; ++pg) {
             const uint32_t g = gpage + pg, stage = g % kStages;
-            mbar_wait(sm.full + stage, (g / kStages) & 1);
+            mbar_wait<CHB_AB_COMPUTE_BACKOFF>(sm.full + stage, (g / kStages) & 1);
             const unsigned char *p = sm.slab + (size_t) stage * kPage;
             const unsigned char *pend = p + min((uint32_t) kPage, total - pg * kPage);
             while (p < pend) {

@@ -7,6 +7,7 @@ T=r02zz
 mkdir -p $O
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > $O/${T}_clocks.csv 2>/dev/null &
 SMI=$!
+python -c 'import __graft_entry__ as g; g.smoke(); print("smoke ok")' > $O/${T}_smoke.log 2>&1
 # 1. headline: cfg4 (default flags), then cfg2 / cfg5 stand-in / cfg3 stand-in / the reference's own benchmark shape
 timeout 1500 python bench.py > $O/${T}_bench_cfg4.json 2> $O/${T}_bench_cfg4.err
 timeout 600 python bench.py --workload cfg2 --no-cpu-baseline > $O/${T}_bench_cfg2.json 2> $O/${T}_bench_cfg2.err
@@ -19,6 +20,7 @@ CHB_LOCAL_KERNEL=0 timeout 900 python bench.py --no-cpu-baseline > $O/${T}_bench
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/${T}_launches_cfg4.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/${T}_bench_under_ncu.json 2>/dev/null
 timeout 1500 ncu --set full --clock-control none --import-source on -k 'regex:chb_(sweep|local|wide)' -s 8 -c 4 -o $O/${T}_solve_cfg4 python scripts/solve_once.py cfg4 f 128 3 > $O/${T}_ncu_cfg4.log 2>&1
 kill $SMI 2>/dev/null
+if [ "${CHB_EVIDENCE_SANITIZER:-1}" = 0 ]; then exit 0; fi
 # 4. compute-sanitizer on a small problem: every executor (local-task kernel, persistent kernel, wide-level kernel)
 for tool in memcheck synccheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool python scripts/solve_once.py ico5 f 128 2 > $O/${T}_sanitizer_${tool}_ico5_f32.log 2>&1

@@ -1,15 +1,6 @@
-# occupancy variants of the persistent kernel (run under gpurun)
-run() { # variant, ring kb, workload, dtype, k
-  if [ "$1" = main ]; then unset CHB_LIB_VARIANT; else export CHB_LIB_VARIANT=$1; fi
-  echo "=== variant $1 ring $2 KB: $3 $4"
-  CHB_RING_KB=$2 timeout 900 python scripts/sweep_experiments.py $3 $4 "$5" 2>&1 | grep -E "^k=|rror"
-}
-run main 36 cfg5 d 128,3
-run d4 36 cfg5 d 128,3
-run d5 27 cfg5 d 128,3
-run d5 20 cfg5 d 128,3
-unset CHB_LIB_VARIANT
-echo "=== defaults"
-timeout 900 python scripts/sweep_experiments.py ico8 f 128,64,32,3,1 2>&1 | grep -E "^k=|rror"
-timeout 900 python scripts/sweep_experiments.py ico9 f 128 2>&1 | grep -E "^k=|rror"
-timeout 900 python scripts/sweep_experiments.py ico6 f 128 2>&1 | grep -E "^k=|rror"
+# inverse super-block length and ticket batching with 6 CTAs per SM (run under gpurun)
+B="CHB_INV_PANELS=64,CHB_INV_PANELS=96,CHB_INV_PANELS=128,CHB_INV_PANELS=256,CHB_INV_PANELS=64+CHB_WIDE_LEVEL=65536,CHB_INV_PANELS=128+CHB_WIDE_LEVEL=65536+CHB_SPLIT_COST=6144+CHB_CHUNK_COST=3072,CHB_INV_PANELS=64+CHB_WIDE_LEVEL=1000000"
+timeout 1500 python scripts/sweep_experiments.py ico9 f 128 0 "" "$B" 2>&1 | grep -E "^k=|rror|^=="
+B="CHB_INV_PANELS=64,CHB_INV_PANELS=128,CHB_INV_PANELS=256,CHB_INV_PANELS=128+CHB_WIDE_LEVEL=65536"
+timeout 900 python scripts/sweep_experiments.py cfg5 d 128 0 "" "$B" 2>&1 | grep -E "^k=|rror|^=="
+timeout 900 python scripts/sweep_experiments.py ico8 f 3 0 "" "CHB_INV_PANELS=32,CHB_INV_PANELS=64,CHB_INV_PANELS=128,CHB_INV_PANELS=256" 2>&1 | grep -E "^k=|rror|^=="
