@@ -497,9 +497,9 @@ GpuSolver::GpuSolver(int device, int elem_size, const HostFactor &L)
             snprintf(buf, sizeof buf, "front e%d w%d lr%d le%d p%d f%d s%d o%d b%d", m_elem, fopt.warps, fopt.local_rows, fopt.local_ext,
                      fopt.panel, fopt.fuse_steps, fopt.split_chunks, fopt.own_chunks, fopt.order_blocks);
         else
-            snprintf(buf, sizeof buf, "panel e%d x%d lr%d le%d lc%d sc%d cc%d a%.4f b%.4f c%d i%d", m_elem, (int) opt.exact_order, opt.local_rows,
+            snprintf(buf, sizeof buf, "panel e%d x%d lr%d le%d lc%d sc%d cc%d a%.4f b%.4f c%d i%d j%d", m_elem, (int) opt.exact_order, opt.local_rows,
                      opt.local_ext, opt.local_cost, opt.split_cost, opt.chunk_cost, opt.relax_alpha, opt.relax_beta, (int) opt.contributions,
-                     opt.inv_panels);
+                     opt.inv_panels, opt.inv_chunk);
         tag = buf;
         cached = m_front ? load_front_images(key, tag, &fimg[0], &fimg[1]) : load_panel_images(key, tag, &img[0], &img[1]);
     }

@@ -70,6 +70,7 @@ ScheduleOptions schedule_options_from_env() {
     o.local_ext = std::max(0, std::min(31, geti("CHB_LOCAL_EXT", o.local_ext)));  // one loader lane per external row
     o.local_cost = std::max(1, geti("CHB_LOCAL_COST", o.local_cost));
     o.inv_panels = std::max(0, std::min(512, geti("CHB_INV_PANELS", o.inv_panels)));
+    o.inv_chunk = std::max(0, geti("CHB_INV_CHUNK", o.inv_chunk));
     o.contributions = geti("CHB_CONTRIBUTIONS", o.contributions ? 1 : 0) != 0;
     o.split_cost = std::max(256, geti("CHB_SPLIT_COST", o.split_cost));
     o.chunk_cost = std::max(256, geti("CHB_CHUNK_COST", o.chunk_cost));
@@ -787,21 +788,36 @@ struct Builder {
                 close_task();
             }
             end_store_r = false;
+            // B(P): x_P = sum over the super-block's panels p of Tinv[P, p] r_p.  Long sums are split into chunk tasks
+            // that run in parallel and park partial tiles in scratch slots (as emit_split_panel does), so a hop of the
+            // critical path at the top of the tree is inv_chunk blocks long, not up to inv_panels.
+            const int wP = S.width(P), oP = S.c0[P] - c_lo;
+            std::vector<int> srcs;  // source panels in this sweep's processing order
+            if (!upper) for (int p = lo; p <= P; ++p) srcs.push_back(p);
+            else for (int p = hi; p >= P; --p) srcs.push_back(p);
+            auto emit_source = [&](int p) {
+                const int op = S.c0[p] - c_lo, wp = S.width(p);
+                if (!upper) emit_inverse_block(p, wP, atask_of_panel[p], [&](int r, int t) { return -tinv[(size_t) (oP + t) * nJ + (op + r)]; });
+                // backward: sources = rows of p visited descending; unknowns = columns of P
+                else emit_inverse_block(p, wP, atask_of_panel[p], [&](int r, int t) { return -tinv[(size_t) (op + wp - 1 - r) * nJ + (oP + t)]; });
+            };
+            const int per_chunk = opt.inv_chunk;
+            int n_chunks = 1;
+            if (per_chunk > 0 && (int) srcs.size() >= 2 * per_chunk) n_chunks = (int) srcs.size() / per_chunk;
+            std::vector<int> slot, task;
+            size_t at = 0;
+            for (int c = 0; c + 1 < n_chunks; ++c) {
+                task.push_back(open_task());
+                emit_begin_zero(P);
+                for (int q = 0; q < per_chunk; ++q) emit_source(srcs[at++]);
+                slot.push_back(img.n_slots++);
+                emit_end_slot(slot.back());
+                close_task();
+            }
             open_task();
             emit_begin_zero(P);
-            const int wP = S.width(P), oP = S.c0[P] - c_lo;
-            if (!upper) {
-                for (int p = lo; p <= P; ++p) {
-                    const int op = S.c0[p] - c_lo;
-                    emit_inverse_block(p, wP, atask_of_panel[p], [&](int r, int t) { return -tinv[(size_t) (oP + t) * nJ + (op + r)]; });
-                }
-            } else {
-                for (int p = hi; p >= P; --p) {
-                    const int op = S.c0[p] - c_lo, wp = S.width(p);
-                    // sources = rows of p visited descending; unknowns = columns of P
-                    emit_inverse_block(p, wP, atask_of_panel[p], [&](int r, int t) { return -tinv[(size_t) (op + wp - 1 - r) * nJ + (oP + t)]; });
-                }
-            }
+            for (size_t c = 0; c < slot.size(); ++c) emit_add_slot(slot[c], task[c]);
+            while (at < srcs.size()) emit_source(srcs[at++]);
             emit_end_store(P, false);
             close_task();
         };

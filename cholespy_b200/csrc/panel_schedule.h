@@ -102,8 +102,10 @@ struct ScheduleOptions {
     double relax_alpha = 1.5; // relaxed panels: stored values <= alpha * non-zeros + beta (1.0 / 0: no fill)
     double relax_beta = 32.0;
     bool contributions = true;// forward sweep, fast mode: local tasks hand their parents ready-made partial sums (REC_ADD_ROWS)
-    int inv_panels = 64;      // consecutive panels of one supernode whose diagonal block is applied as an explicit
+    int inv_panels = 256;     // consecutive panels of one supernode whose diagonal block is applied as an explicit
                               // inverse (fast mode only; < 2: off).  See "inverse super-blocks" below.
+    int inv_chunk = 8;        // inverse-apply tasks of >= 2 * inv_chunk blocks are split into parallel chunk tasks of inv_chunk
+                              // blocks + a final task (0: never)
     bool exact_order = false; // true: chunks are CHAINED (reference summation order kept bit for bit)
                               // false: chunks run in parallel and are summed in a fixed order
 };
