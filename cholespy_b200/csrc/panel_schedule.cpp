@@ -2,6 +2,8 @@
 #include "panel_schedule.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -755,13 +757,43 @@ struct Builder {
                     present += 1;
                 }
             img.n_values += present;  // the super-block's own entries are consumed through the inverse
+            // Column c of the inverse: T x = e_c by forward substitution, x_i = (e_ci - sum_{q<i} T[i,q] x_q) / T[i,i] with q
+            // ascending.  Columns are independent; they are computed in blocks of 32 (handed out to the host threads by
+            // an atomic counter), row by row, so the inner loop runs over contiguous memory -- a top separator is one
+            // super-block of a few thousand columns, n^3 / 3 multiply-adds.
             tinv.assign((size_t) nJ * nJ, 0.0);
-            for (int c = 0; c < nJ; ++c) {  // column c of the inverse: T x = e_c by forward substitution
-                for (int i = c; i < nJ; ++i) {
-                    double acc = i == c ? 1.0 : 0.0;
-                    for (int q = c; q < i; ++q) acc -= T[(size_t) i * nJ + q] * tinv[(size_t) q * nJ + c];
-                    tinv[(size_t) i * nJ + c] = acc / T[(size_t) i * nJ + i];
+            constexpr int kColBlock = 32;
+            const int n_col_blocks = (nJ + kColBlock - 1) / kColBlock;
+            std::atomic<int> next{0};
+            auto worker = [&]() {
+                for (;;) {
+                    const int cb = next.fetch_add(1);
+                    if (cb >= n_col_blocks) return;
+                    const int c0 = cb * kColBlock, c1 = std::min(nJ, c0 + kColBlock);
+                    for (int i = c0; i < nJ; ++i) {
+                        double *xi = &tinv[(size_t) i * nJ];
+                        const double *ti = &T[(size_t) i * nJ];
+                        const int ce = std::min(c1, i + 1);  // the inverse is lower triangular
+                        if (i < c1) xi[i] = 1.0;
+                        for (int q = c0; q < i; ++q) {
+                            const double t = ti[q];
+                            if (t == 0.0) continue;
+                            const double *xq = &tinv[(size_t) q * nJ];
+                            const int qe = std::min(ce, q + 1);
+                            for (int c = c0; c < qe; ++c) xi[c] -= t * xq[c];
+                        }
+                        const double d = ti[i];
+                        for (int c = c0; c < ce; ++c) xi[c] /= d;
+                    }
                 }
+            };
+            const int n_threads = (int) std::max(1u, std::min(16u, std::min((unsigned) n_col_blocks, std::thread::hardware_concurrency())));
+            if (n_threads <= 1 || nJ < 256) {
+                worker();
+            } else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+                for (std::thread &t : pool) t.join();
             }
         };
         // panel P of the inverse super-block [lo, hi]: task(s) A (residual) then task B (inverse apply)
