@@ -37,6 +37,24 @@ def test_fast_schedule_within_tolerance(name, dtype, oracle_mod, native_lib):
     assert max_rel_err(x, x_ref) < TOL[np.dtype(dtype)], name
 
 
+# Inverse super-blocks (panel_schedule.h): runs of inv_panels panels of one supernode applied through an explicit inverse,
+# the inverse-apply tasks split into chunk tasks of inv_chunk blocks that park partial tiles in scratch slots.  Small
+# settings make both mechanisms fire on the small test problems (the defaults, 256 / 8, need separators of >= 256 columns).
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("settings", [("4", "2"), ("3", "1"), ("64", "0"), ("1", "8")])
+@pytest.mark.parametrize("name", ["ico5", "grid3d-10", "grid2d-40", "localspd-30"])
+def test_inverse_super_block_settings(name, settings, dtype, oracle_mod, native_lib, monkeypatch):
+    monkeypatch.setenv("CHB_INV_PANELS", settings[0])
+    monkeypatch.setenv("CHB_INV_CHUNK", settings[1])
+    p = problems.build_problem(name)
+    perm, cp, ri, v = factorize(native_lib, p["n"], p["ii"], p["jj"], p["x"], p["fmt"])
+    b = np.random.default_rng(6).random((p["n"], 5)).astype(dtype)
+    x_ref = oracle_mod.solve(cp, ri, v, perm, b)
+    x, fwd, bwd = oracle_mod.schedule_solve(native_lib, cp, ri, v, perm, b, exact_order=0)
+    assert fwd["n_values"] == len(ri) and bwd["n_values"] == len(ri)  # every factor entry is used exactly once
+    assert max_rel_err(x, x_ref) < TOL[np.dtype(dtype)], (name, settings)
+
+
 def _random_spd(n, density, seed):
     """A = B B' + n I with a random sparse B plus a band (irregular elimination trees: chains, stars, wide fronts)."""
     import scipy.sparse as sp
