@@ -87,8 +87,9 @@ int padded_rhs(int k) { return (k + 3) & ~3; }  // row stride of the work vector
 int sweep_warps(int k) { return (k + 31) / 32; }  // compute warps: one per 32 RHS columns (+ 1 loader warp).  Wider lanes
 // (2 or 4 columns per lane, fewer warps) were measured slower on ico8 and ico9 at 64..128 RHS: tasks are latency-bound.
 
-// Rows of the shared-memory row ring: room for the largest local task plus one full block, at least about 36 KB
-// (four CTAs per SM at 128 single-precision right-hand sides; measured: occupancy beats ring depth).
+// Rows of the shared-memory row ring: room for the largest local task the persistent kernel still executes (none by
+// default: they run in the local-task kernel) plus one full block, at least 20 KB (f32: six CTAs per SM at 128
+// right-hand sides) / 36 KB (f64: four); measured: occupancy beats ring depth.
 int sweep_ring_rows(int elem, int k, int local_rows) {
     const int row_bytes = padded_rhs(k) * elem;
     // f32: six CTAs per SM at 128 columns (sweep.cuh: CHB_SWEEP_MIN_CTAS_F32) leave 20 KB next to the four slab pages

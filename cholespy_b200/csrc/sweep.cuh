@@ -24,11 +24,11 @@
 //     mbarrier, multiply out of shared memory (factor values broadcast with LDS.128, source rows
 //     conflict-free), and hand the ring rows back through an "empty" mbarrier;
 //   * the tile (<= 16 rows) of the panel being solved lives in registers, one RHS column per lane;
-//   * LOCAL tasks (complete subtrees of small panels, most of the rows): the subtree's right-hand
-//     side rows and the external rows it reads are staged into the row ring by the loader as ONE
-//     record (while the compute warps are still busy with earlier tasks), every record of the task
-//     then works in place in shared memory, and the solved rows are written back once -- no
-//     per-row round trips to L2;
+//   * LOCAL tasks (complete subtrees of small panels, most of the rows) are executed by their own
+//     kernel by default (local_sweep.cuh); this kernel keeps the code for them (CHB_LOCAL_KERNEL=0, or
+//     tasks over that kernel's budget): the subtree's right-hand side rows and the external rows it
+//     reads are staged into the row ring by the loader as ONE record, every record of the task then
+//     works in place in shared memory, and the solved rows are written back once;
 //   * dependencies: one epoch-valued ready flag per TASK (ld.acquire.gpu / st.release.gpu after a
 //     named barrier of the compute warps); flags are never cleared (the epoch is the solve counter);
 //   * the work vector `tmp` and the partial-tile scratch have their row stride padded to 4 elements
