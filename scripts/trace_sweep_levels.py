@@ -25,8 +25,8 @@ for key in ("fwd", "bwd"):
         print("  %5d %6d %6.1f %12.1f %12.1f %12.1f %12.1f %12.1f" % (L, m.sum(), byt[m].sum() / 1e6, st[m].min(), en[m].max(),
                                                                   en[m].max() - st[m].min(), d.mean(), np.percentile(d, 99)))
     order = np.argsort(np.where(ran, st, np.inf))[:int(ran.sum())]
-    q = [st[order[int(f * (len(st) - 1))]] for f in (0.25, 0.5, 0.75, 0.9, 0.99, 1.0)]
+    q = [st[order[int(f * (len(order) - 1))]] for f in (0.25, 0.5, 0.75, 0.9, 0.99, 1.0)]
     print("  task start times at 25/50/75/90/99/100%% of the tasks: %s us" % ", ".join("%.0f" % v for v in q))
-    bq = np.cumsum(byt[order]) / byt.sum()
+    bq = np.cumsum(byt[order]) / byt[order].sum()
     for f in (0.5, 0.9, 0.99):
-        print("  %.0f%% of the slab bytes started by %.0f us" % (100 * f, st[order[np.searchsorted(bq, f)]]))
+        print("  %.0f%% of the slab bytes started by %.0f us" % (100 * f, st[order[min(np.searchsorted(bq, f), len(order) - 1)]]))
