@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -201,6 +202,7 @@ struct Builder {
     std::vector<Contribution> contrib_of_task;
     bool contributions() const { return !upper && !opt.exact_order && opt.contributions; }
     int64_t stat_blocks_from_local = 0, stat_rows_from_local = 0, stat_vals_from_local = 0, stat_blocks_nonlocal = 0, stat_rows_nonlocal = 0, stat_ext_rows = 0;
+    double stat_inverse_s = 0, stat_inverse_panel_s = 0, stat_inverse_apply_s = 0;  // host seconds (CHB_SCHED_STATS)
     bool end_store_r = false;
     std::vector<int> atask_of_panel;
 
@@ -747,6 +749,7 @@ struct Builder {
         int tinv_lo = -1;
         auto prepare_inverse = [&](int lo, int hi) {
             if (tinv_lo == lo) return;
+            const auto t_inv0 = std::chrono::steady_clock::now();
             tinv_lo = lo;
             const int c_lo = S.c0[lo], nJ = S.c0[hi + 1] - c_lo;
             std::vector<double> T((size_t) nJ * nJ, 0.0);
@@ -766,24 +769,27 @@ struct Builder {
             const int n_col_blocks = (nJ + kColBlock - 1) / kColBlock;
             std::atomic<int> next{0};
             auto worker = [&]() {
+                std::vector<double> X;  // this column block of the inverse, rows [c0, nJ) x kColBlock, contiguous
                 for (;;) {
                     const int cb = next.fetch_add(1);
                     if (cb >= n_col_blocks) return;
-                    const int c0 = cb * kColBlock, c1 = std::min(nJ, c0 + kColBlock);
+                    const int c0 = cb * kColBlock, c1 = std::min(nJ, c0 + kColBlock), wb = c1 - c0;
+                    X.assign((size_t) (nJ - c0) * kColBlock, 0.0);
                     for (int i = c0; i < nJ; ++i) {
-                        double *xi = &tinv[(size_t) i * nJ];
+                        double *xi = &X[(size_t) (i - c0) * kColBlock];
                         const double *ti = &T[(size_t) i * nJ];
-                        const int ce = std::min(c1, i + 1);  // the inverse is lower triangular
-                        if (i < c1) xi[i] = 1.0;
+                        const int ce = std::min(wb, i - c0 + 1);  // the inverse is lower triangular
+                        if (i < c1) xi[i - c0] = 1.0;
                         for (int q = c0; q < i; ++q) {
                             const double t = ti[q];
                             if (t == 0.0) continue;
-                            const double *xq = &tinv[(size_t) q * nJ];
-                            const int qe = std::min(ce, q + 1);
-                            for (int c = c0; c < qe; ++c) xi[c] -= t * xq[c];
+                            const double *xq = &X[(size_t) (q - c0) * kColBlock];
+                            const int qe = std::min(ce, q - c0 + 1);
+                            for (int c = 0; c < qe; ++c) xi[c] -= t * xq[c];
                         }
                         const double d = ti[i];
-                        for (int c = c0; c < ce; ++c) xi[c] /= d;
+                        double *out = &tinv[(size_t) i * nJ + c0];
+                        for (int c = 0; c < ce; ++c) out[c] = xi[c] = xi[c] / d;
                     }
                 }
             };
@@ -795,9 +801,12 @@ struct Builder {
                 for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
                 for (std::thread &t : pool) t.join();
             }
+            stat_inverse_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_inv0).count();
         };
         // panel P of the inverse super-block [lo, hi]: task(s) A (residual) then task B (inverse apply)
         auto emit_inverse_panel = [&](int P) {
+            const auto t_ip0 = std::chrono::steady_clock::now();
+            struct Acc { double &s; std::chrono::steady_clock::time_point t0; ~Acc() { s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } } acc_guard{stat_inverse_panel_s, t_ip0};
             const int lo = sb_lo[P], hi = sb_hi[P];
             prepare_inverse(lo, hi);
             const int c_lo = S.c0[lo], nJ = S.c0[hi + 1] - c_lo;
@@ -820,6 +829,8 @@ struct Builder {
                 close_task();
             }
             end_store_r = false;
+            const auto t_b0 = std::chrono::steady_clock::now();
+            struct AccB { double &s; std::chrono::steady_clock::time_point t0; ~AccB() { s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } } accb_guard{stat_inverse_apply_s, t_b0};
             // B(P): x_P = sum over the super-block's panels p of Tinv[P, p] r_p.  Long sums are split into chunk tasks
             // that run in parallel and park partial tiles in scratch slots (as emit_split_panel does), so a hop of the
             // critical path at the top of the tree is inv_chunk blocks long, not up to inv_panels.
@@ -900,7 +911,12 @@ void build_sweep_image(const HostFactor &L, const PanelStructure &S, int elem_si
     img.page_bytes = page_bytes_for(elem_size);
     img.slab.reserve((size_t) ((double) L.nnz() * elem_size * 1.3) + (size_t) S.n_panels * 160 + 4096);
     Builder b(L, S, opt, img);
+    const auto t_run0 = std::chrono::steady_clock::now();
     b.run();
+    const double run_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run0).count();
+    if (std::getenv("CHB_SCHED_STATS"))
+        fprintf(stderr, "[sched %s] build %.2f s, of which inverse super-block panels %.2f s (triangle inverses %.2f s, inverse-apply tasks %.2f s)\n",
+                upper ? "bwd" : "fwd", run_s, b.stat_inverse_panel_s, b.stat_inverse_s, b.stat_inverse_apply_s);
     if (std::getenv("CHB_SCHED_STATS"))
         fprintf(stderr, "[sched %s] non-local blocks %lld (rows %lld), of which from local producers %lld (rows %lld, values %lld); ext rows of local tasks %lld\n",
                 upper ? "bwd" : "fwd", (long long) b.stat_blocks_nonlocal, (long long) b.stat_rows_nonlocal, (long long) b.stat_blocks_from_local,
