@@ -202,7 +202,7 @@ struct Builder {
     std::vector<Contribution> contrib_of_task;
     bool contributions() const { return !upper && !opt.exact_order && opt.contributions; }
     int64_t stat_blocks_from_local = 0, stat_rows_from_local = 0, stat_vals_from_local = 0, stat_blocks_nonlocal = 0, stat_rows_nonlocal = 0, stat_ext_rows = 0;
-    double stat_inverse_s = 0, stat_inverse_panel_s = 0, stat_inverse_apply_s = 0;  // host seconds (CHB_SCHED_STATS)
+    double stat_inverse_s = 0, stat_inverse_panel_s = 0, stat_inverse_apply_s = 0, stat_local_s = 0, stat_fill_s = 0, stat_prep_s = 0;  // host seconds (CHB_SCHED_STATS)
     bool end_store_r = false;
     std::vector<int> atask_of_panel;
 
@@ -318,14 +318,21 @@ struct Builder {
     void emit_add_slot(int slot, int dep_task) { w.record(REC_ADD_SLOT, 0, (uint32_t) slot << 8, wait_code(dep_task), 0); }
     void emit_end_slot(int slot) { w.record(REC_END_SLOT, 0, (uint32_t) slot << 8, 0, 0); }
 
+    // A block record's header and masks are functions of the structure alone; its values (a sparse -> dense gather and
+    // a re-layout) are the expensive part of building an image and independent of everything else: emit_block
+    // reserves the record, fill_block writes the payload -- for all blocks at the end of run(), by all host threads.
+    struct PendingBlock {
+        size_t off;
+        int64_t b;
+    };
+    std::vector<PendingBlock> pending_blocks;
+
     void emit_block(int P, int64_t b) {
-        const int p = S.b_src[b], t = S.b_tgt[b], q0 = S.b_q0[b];
+        const int p = S.b_src[b], t = S.b_tgt[b];
         const uint32_t rows = S.b_mask[b];
         const int nr = popc16(rows);
         const size_t es = (size_t) img.elem;
         img.n_blocks += 1;
-        double buf[kPanelWidth][kPanelWidth];  // [row of the block][column of p]
-        img.n_values += gather_block(p, q0, nr, buf);
         // One layout for every block ("grouped source-major"): per source, in sweep order, the values of the
         // 4-target GROUPS that contain at least one target (zero-filled inside a group).  Explicit zeros
         // are bit-neutral under fused multiply-subtract.
@@ -333,24 +340,69 @@ struct Builder {
         const uint32_t tmask = upper ? (1u << wd) - 1 : rows;   // unknowns: columns of p (backward) / rows of t present (forward)
         const uint32_t smask = upper ? rows : (1u << wd) - 1;   // sources: rows of t present (backward) / columns of p (forward)
         const int ns = upper ? nr : wd;
-        int group_rank[4], ng = 0;
-        for (int g = 0; g < 4; ++g) group_rank[g] = (tmask >> (4 * g) & 0xf) ? ng++ : -1;
+        int ng = 0;
+        for (int g = 0; g < 4; ++g) ng += (tmask >> (4 * g) & 0xf) ? 1 : 0;
         const int stride = 4 * ng;
         const uint32_t wait = wait_code(task_of_panel[upper ? t : p]);
         (void) P;
         if (!upper && !local_root.empty() && local_root[p] >= 0) stat_blocks_from_local += 1, stat_rows_from_local += ns, stat_vals_from_local += (int64_t) ns * popc16(tmask);
         if (!upper) stat_blocks_nonlocal += 1, stat_rows_nonlocal += ns;
         const size_t off = w.record(REC_BLOCK_D4, S.c0[upper ? t : p], smask | tmask << 16, wait, es * (size_t) ns * (size_t) stride);
+        pending_blocks.push_back(PendingBlock{off, b});
+        img.n_stored_values += (int64_t) ns * stride;
+    }
+    // The payload of one reserved block record; returns the number of factor entries it holds.  Touches only its own
+    // bytes of the slab (which no longer grows when this runs).
+    int fill_block(const PendingBlock &pb) {
+        const int64_t b = pb.b;
+        const int p = S.b_src[b], q0 = S.b_q0[b];
+        const uint32_t rows = S.b_mask[b];
+        const int nr = popc16(rows);
+        double buf[kPanelWidth][kPanelWidth];  // [row of the block][column of p]
+        const int present = gather_block(p, q0, nr, buf);
+        const int wd = S.width(p);
+        const uint32_t tmask = upper ? (1u << wd) - 1 : rows;
+        const int ns = upper ? nr : wd;
+        int group_rank[4], ng = 0;
+        for (int g = 0; g < 4; ++g) group_rank[g] = (tmask >> (4 * g) & 0xf) ? ng++ : -1;
+        const int stride = 4 * ng;
         // backward: sources visited in DESCENDING row order (the reference walks a row of L' from its end backwards)
         for (int r = 0; r < ns; ++r) {
             int q = 0;  // rank of the target among the block's rows (forward)
             for (int tt = 0; tt < kPanelWidth; ++tt) {
                 if (!(tmask >> tt & 1)) continue;
                 const double v = upper ? buf[nr - 1 - r][tt] : buf[q++][r];
-                w.put_value(off, (size_t) r * stride + 4 * group_rank[tt >> 2] + (tt & 3), v);
+                w.put_value(pb.off, (size_t) r * stride + 4 * group_rank[tt >> 2] + (tt & 3), v);
             }
         }
-        img.n_stored_values += (int64_t) ns * stride;
+        return present;
+    }
+    void fill_pending_blocks() {
+        const size_t n = pending_blocks.size();
+        std::atomic<size_t> next{0};
+        std::atomic<int64_t> present{0};
+        constexpr size_t kBatch = 256;
+        auto worker = [&]() {
+            int64_t mine = 0;
+            for (;;) {
+                const size_t lo = next.fetch_add(kBatch);
+                if (lo >= n) break;
+                const size_t hi = std::min(n, lo + kBatch);
+                for (size_t i = lo; i < hi; ++i) mine += fill_block(pending_blocks[i]);
+            }
+            present += mine;
+        };
+        const unsigned n_threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));  // both sweeps are built at once
+        if (n_threads <= 1 || n < 4 * kBatch) {
+            worker();
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+            for (std::thread &t : pool) t.join();
+        }
+        img.n_values += present.load();
+        pending_blocks.clear();
+        pending_blocks.shrink_to_fit();
     }
 
     // Fast mode: the triangle as a dense wp x wp matrix (wp = 1 or round4(w)) in pivot order with
@@ -657,6 +709,7 @@ struct Builder {
     }
 
     void run() {
+        const auto t_prep0 = std::chrono::steady_clock::now();
         const int np = S.n_panels;
         std::vector<int64_t> blocks;
         // LOCAL tasks are COMPLETE SUBTREES of the panel elimination tree (a contiguous index range,
@@ -865,6 +918,7 @@ struct Builder {
             close_task();
         };
 
+        stat_prep_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_prep0).count();
         int i = 0;
         while (i < np) {
             // [lo, hi] = the next run of panels forming one task, in this sweep's processing order
@@ -880,7 +934,9 @@ struct Builder {
             }
             i += hi - lo + 1;
             if (root_of[hi] >= 0) {
+                const auto t_l0 = std::chrono::steady_clock::now();
                 emit_local_task(lo, hi, blocks);
+                stat_local_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_l0).count();
                 continue;
             }
             if (sb_lo[lo] >= 0) {
@@ -896,6 +952,9 @@ struct Builder {
             emit_panel(lo, blocks);
             close_task();
         }
+        const auto t_f0 = std::chrono::steady_clock::now();
+        fill_pending_blocks();
+        stat_fill_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_f0).count();
     }
 };
 
@@ -915,8 +974,8 @@ void build_sweep_image(const HostFactor &L, const PanelStructure &S, int elem_si
     b.run();
     const double run_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run0).count();
     if (std::getenv("CHB_SCHED_STATS"))
-        fprintf(stderr, "[sched %s] build %.2f s, of which inverse super-block panels %.2f s (triangle inverses %.2f s, inverse-apply tasks %.2f s)\n",
-                upper ? "bwd" : "fwd", run_s, b.stat_inverse_panel_s, b.stat_inverse_s, b.stat_inverse_apply_s);
+        fprintf(stderr, "[sched %s] build %.2f s: preparation %.2f s, local tasks %.2f s, inverse super-block panels %.2f s (triangle inverses %.2f s, inverse-apply tasks %.2f s), block payloads %.2f s\n",
+                upper ? "bwd" : "fwd", run_s, b.stat_prep_s, b.stat_local_s, b.stat_inverse_panel_s, b.stat_inverse_s, b.stat_inverse_apply_s, b.stat_fill_s);
     if (std::getenv("CHB_SCHED_STATS"))
         fprintf(stderr, "[sched %s] non-local blocks %lld (rows %lld), of which from local producers %lld (rows %lld, values %lld); ext rows of local tasks %lld\n",
                 upper ? "bwd" : "fwd", (long long) b.stat_blocks_nonlocal, (long long) b.stat_rows_nonlocal, (long long) b.stat_blocks_from_local,
